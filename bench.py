@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py - sentences/sec of the SNR-sweep encode -> channel -> greedy decode -> BLEU counts path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--units U]
+
+Workload (BASELINE.json configs[1]): Star-Transformer DeepSC-GAN (`Transeiver_Star`, SE/SD, cycle_num 8)
+over AWGN, SNR sweep 0..18 dB, greedy argmax decode of 30 steps, BLEU n-gram counts.  One "step" = one pass of
+the path over a batch of U 64-sentence synthetic Europarl-shape units (U = 38 by default: every SNR point of the
+sweep twice), weights random-init (the reference's checkpoints are missing).  One "sentence" = one sentence
+evaluated at one SNR point.  N > 1: each rank processes its own U units (weak scaling, no data-path collective);
+the int32 BLEU count table is all-gathered at the end of every step.
+
+value   : inputs resident in HBM, CUDA-event time, max over ranks.
+e2e     : same metric through the public API with HOST buffers: per step the ids are copied from pinned host
+          memory and the BLEU counts are read back, both inside the timed region.
+roofline: the dominant kernel (the Dense GEMM of the star cycles), FLOPs per launch / mean event-timed launch.
+cpu_baseline / --impl reference: the CPU oracle (PyTorch restatement of the reference; the TensorFlow reference
+          itself cannot run here) on a bounded sample of the same workload, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "sentences/sec for SNR-sweep encode->channel->decode+BLEU"
+UNIT = "sentences/s"
+SNRS = list(range(19))
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_oracle_rate(n_units: int, first_unit: int = 0):
+    """Oracle greedy decode + BLEU counts over ``n_units`` units (one SNR point each, cycling the sweep)."""
+    from deepsc_gan_b200.dataset.synthetic import synthetic_unit
+    from oracle import bleu_oracle, deepsc_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    spec = O.Spec("Transeiver_Star")
+    P = O.init_params(spec, seed=2024)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for u in range(n_units):
+            inp = synthetic_unit(first_unit + u).long()
+            g = torch.Generator().manual_seed(7 + u)
+            z = torch.randn(64, 31, 16, generator=g)
+            ids = O.greedy_decode_noattack(P, spec, inp, 0.0, "AWGN", O.snr_to_noise(SNRS[u % 19]), z)
+            bleu_oracle.bleu_counts(inp.numpy(), ids.numpy())
+    dt = time.perf_counter() - t0
+    return 64 * n_units / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle timed on the host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import deepsc_gan_b200  # noqa: F401
+    units = args.ref_units
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_rate(1)
+    times = []
+    for s in range(args.steps):
+        rate, dt = cpu_oracle_rate(units, first_unit=s * units)
+        times.append(dt)
+    T = sum(times)
+    value = 64 * units * args.steps / T
+    sample = f"{units} units x {args.steps} steps of the workload (64 sentences each, SNR points cycled), KV-free oracle greedy"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(units, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(units: int, world: int):
+    return {"workload": "Transeiver_Star (SE/SD, cycle_num=8, d_model=128, 8 heads, vocab 22234) AWGN SNR sweep 0-18 dB, "
+                        "greedy decode 30 steps + BLEU counts",
+            "units_per_step_per_gpu": units, "sentences_per_unit": 64, "seq_len": 31, "snr_points_db": "0..18",
+            "sharding": f"{world} rank(s) x {units} units, unit-granular, no data-path collective",
+            "l2_policy": "per-step working set (activations + logits workspace) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--units", type=int, default=38, help="64-sentence units per step per GPU")
+    ap.add_argument("--ref-units", type=int, default=4, help="units per step of the CPU reference arm")
+    ap.add_argument("--cpu-units", type=int, default=8, help="units of the cpu_baseline sample (N=1 only)")
+    ap.add_argument("--prec", type=int, default=0, help="0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import deepsc_gan_b200  # noqa: F401
+    from deepsc_gan_b200 import _lib, sweep
+    from deepsc_gan_b200.dataset.synthetic import synthetic_units
+    from deepsc_gan_b200.models import Transeiver_Star, modules
+    from deepsc_gan_b200.utlis.parameters import para_config
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    modules.set_precision(args.prec)
+    peaks = load_peaks()
+
+    cfg = para_config([])
+    torch.manual_seed(2024)
+    net = Transeiver_Star(cfg).to(dev).eval()
+    U, S = args.units, args.units * 64
+    runner = sweep.SweepRunner(net, U, channel="AWGN", seed=1234 + rank)
+    n_std_host = torch.tensor([sweep.snr_to_noise(SNRS[(rank * U + u) % 19]) for u in range(U)], dtype=torch.float32)
+    n_std = n_std_host.to(dev)
+    total_steps = args.warmup + args.steps
+    # distinct inputs per step (and per rank); pinned on the host for the e2e leg
+    host_inputs = [synthetic_units((rank * total_steps + s) * U, U).pin_memory() for s in range(total_steps)]
+    dev_inputs = [h.to(dev) for h in host_inputs]
+    counts_host = torch.empty((S, 10), dtype=torch.int32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(s):
+        ids, counts = runner.run(dev_inputs[s], n_std)
+        return sweep.gather_counts(counts)
+
+    def step_e2e(s):
+        inp = host_inputs[s].to(dev, non_blocking=True)
+        ids, counts = runner.run(inp, n_std)
+        table = sweep.gather_counts(counts)
+        counts_host.copy_(counts, non_blocking=True)
+        return table
+
+    # ---- device-resident leg -------------------------------------------------------------------------------
+    for s in range(args.warmup):
+        step_resident(s)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    _lib.STATS["launches"] = 0
+    _lib.PROFILE = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s in range(args.warmup, total_steps):
+        step_resident(s)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    t_ms = ev0.elapsed_time(ev1)
+    launches = _lib.STATS["launches"]
+    prof, _lib.PROFILE = _lib.PROFILE, None
+
+    # ---- end-to-end leg (host buffers in, counts out) ------------------------------------------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.warmup, total_steps):
+        step_e2e(s)
+    e1.record()
+    barrier()
+    t_e2e_ms = e0.elapsed_time(e1)
+
+    if world > 1:
+        tt = torch.tensor([t_ms, t_e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms, t_e2e_ms = float(tt[0]), float(tt[1])
+
+    # ---- roofline of the dominant kernel: the [S*32,128] x [128,384] projection GEMM of the star cycles ------
+    dom = [(a.elapsed_time(b), M, K, N) for a, b, M, K, N in prof if K == 128 and N == 384 and M == S * 32]
+    allg = [(a.elapsed_time(b), M, K, N) for a, b, M, K, N in prof]
+    gemm_ms = sum(t for t, *_ in allg)
+    roof = None
+    if dom:
+        mean_ms = sum(t for t, *_ in dom) / len(dom)
+        flops = 2.0 * S * 32 * 128 * 384
+        achieved = flops / (mean_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "dsc_linear [S*32,128]x[128,384] (star-cycle QKV projection)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
+                "launches_timed": len(dom), "mean_launch_ms": mean_ms, "flops_per_launch": flops,
+                "gemm_share_of_step": gemm_ms / t_ms, "arith": {0: "fp32 FFMA", 1: "bf16x3 tcgen05", 2: "bf16 tcgen05"}[args.prec]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sentences = S * world * args.steps
+    value = sentences / (t_ms * 1e-3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {0: "f32", 1: "bf16x3 (fp32-class)", 2: "bf16"}[args.prec], "data": "synthetic",
+            "config": workload_config(U, world), "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": sentences / (t_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": S * 31 * 4,
+                    "d2h_bytes_per_step": S * 10 * 4},
+            "roofline": roof}
+    if world == 1 and not args.no_cpu_baseline:
+        rate, dt = cpu_oracle_rate(args.cpu_units)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{args.cpu_units} units (512 sentences) of the same workload, oracle greedy "
+                                          f"(last-position logits), {dt:.1f} s wall"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

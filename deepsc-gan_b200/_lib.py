@@ -1,0 +1,326 @@
+"""ctypes binding of libdeepsc_b200.so (the C ABI declared in include/deepsc_b200.h).
+
+PyTorch is used here for device memory and streams only: every wrapper takes CUDA tensors,
+passes raw device pointers plus the current stream, and raises if the library is missing or
+returns an error.  There is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdeepsc_b200.so")
+
+_lib: Optional[C.CDLL] = None
+
+i32, i64, u64, f32, vp = C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
+
+_SIGNATURES = {
+    "dsc_version": (C.c_int, []),
+    "dsc_last_error": (C.c_char_p, []),
+    "dsc_device_arch": (C.c_int, []),
+    "dsc_embed": (C.c_int, [vp, i64, vp, i32, vp, vp, i64, i32, i32, i32, vp]),
+    "dsc_linear": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "dsc_add_layernorm": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    "dsc_star_pack": (C.c_int, [vp, vp, i32, vp]),
+    "dsc_star_satellite_attn": (C.c_int, [vp, vp, vp, i32, vp]),
+    "dsc_star_relay_attn": (C.c_int, [vp, vp, i32, i32, vp, i32, vp]),
+    "dsc_mha_attention": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,
+                                    i32, i32, i32, vp]),
+    "dsc_unit_sumsq": (C.c_int, [vp, vp, i32, i64, vp]),
+    "dsc_power_normalize": (C.c_int, [vp, vp, f32, vp, i32, i64, vp]),
+    "dsc_channel": (C.c_int, [vp, vp, f32, vp, u64, u64, vp, vp, f32, vp, vp, vp, i32, vp, vp, i32, i64, vp]),
+    "dsc_vocab_argmax": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp]),
+    "dsc_vocab_argmax_workspace": (C.c_int64, [i32, i32]),
+    "dsc_argmax_rows": (C.c_int, [vp, i64, vp, i64, i32, i32, vp]),
+    "dsc_masked_ce_rows": (C.c_int, [vp, i64, vp, vp, i32, i32, vp]),
+    "dsc_bleu_counts": (C.c_int, [vp, i32, vp, i32, vp, i32, vp]),
+    "dsc_fgm_normalize": (C.c_int, [vp, vp, f32, i32, i32, i32, vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no GPU needed for this step) and set the prototypes."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "deepsc_gan_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+class DscError(RuntimeError):
+    pass
+
+
+# kernel launches issued through this binding (bench.py reports them as gpu_launches)
+_KERNELS_PER_CALL = {"dsc_vocab_argmax": 2}
+STATS = {"launches": 0}
+# when set to a list, linear() appends (start_event, end_event, M, K, N) for roofline accounting
+PROFILE = None
+
+
+def _check(rc: int, what: str) -> None:
+    STATS["launches"] += _KERNELS_PER_CALL.get(what, 1)
+    if rc != 0:
+        msg = load().dsc_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(msg or what)
+        raise DscError(f"{what} failed ({rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("deepsc_gan_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype}")
+    return t
+
+
+# --------------------------------------------------------------------------- wrappers
+def version() -> int:
+    return load().dsc_version()
+
+
+def embed(ids: torch.Tensor, table: torch.Tensor, pos_table: torch.Tensor, pos0: int = 0,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ids [n, len] int32 (last-dim stride 1, any row stride) -> [n, len, 128]."""
+    _need_cuda(ids, table, pos_table)
+    assert ids.dtype == torch.int32 and ids.dim() == 2 and (ids.shape[1] == 1 or ids.stride(1) == 1)
+    n, ln = ids.shape
+    if out is None:
+        out = torch.empty((n, ln, 128), device=ids.device, dtype=torch.float32)
+    _check(load().dsc_embed(ids.data_ptr(), ids.stride(0), _f32(table).data_ptr(), table.shape[0],
+                            pos_table.data_ptr(), out.data_ptr(), 128, n, ln, pos0, _stream()), "dsc_embed")
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0,
+           out: Optional[torch.Tensor] = None, n: Optional[int] = None, row_mod: int = 0, row_skip: int = 0,
+           prec: int = 0) -> torch.Tensor:
+    """y = act(x @ w + bias).  x [M, K] (row stride free), w [K, >=N] Keras layout, out [M, N] (row stride free)."""
+    _need_cuda(x, w, bias, out)
+    assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[1] if n is None else n
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    assert out.dim() == 2 and out.shape[0] == M and out.shape[1] == N and out.stride(1) == 1
+    if PROFILE is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _check(load().dsc_linear(_f32(x).data_ptr(), x.stride(0), _f32(w).data_ptr(), w.stride(0), _ptr(bias),
+                             out.data_ptr(), out.stride(0), M, K, N, act, row_mod, row_skip, prec, _stream()),
+           "dsc_linear")
+    if PROFILE is not None:
+        ev1.record()
+        PROFILE.append((ev0, ev1, M, K, N))
+    return out
+
+
+def add_layernorm(x: torch.Tensor, res: Optional[torch.Tensor], gamma_a, beta_a, gamma_b=None, beta_b=None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x, res, out: [groups, rows, 128] views whose rows are contiguous within a group (group stride free)."""
+    _need_cuda(x, res, out)
+    assert x.dim() == 3 and x.shape[2] == 128 and x.stride(2) == 1 and x.stride(1) == 128
+    g, r, _ = x.shape
+    if out is None:
+        out = torch.empty((g, r, 128), device=x.device, dtype=torch.float32)
+    assert out.shape == x.shape and out.stride(1) == 128
+    if res is not None:
+        assert res.shape == x.shape and res.stride(1) == 128 and res.stride(2) == 1
+    _check(load().dsc_add_layernorm(x.data_ptr(), x.stride(0), _ptr(res), 0 if res is None else res.stride(0),
+                                    gamma_a.data_ptr(), beta_a.data_ptr(), _ptr(gamma_b), _ptr(beta_b),
+                                    out.data_ptr(), out.stride(0), g * r, r, _stream()), "dsc_add_layernorm")
+    return out
+
+
+def star_pack(src: torch.Tensor, tile: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[n, 31, 128] contiguous -> star tile [n, 32, 128] with row 31 = mean of the 31 rows."""
+    _need_cuda(src)
+    assert src.is_contiguous() and src.shape[1:] == (31, 128)
+    n = src.shape[0]
+    if tile is None:
+        tile = torch.empty((n, 32, 128), device=src.device, dtype=torch.float32)
+    _check(load().dsc_star_pack(_f32(src).data_ptr(), tile.data_ptr(), n, _stream()), "dsc_star_pack")
+    return tile
+
+
+def star_satellite_attn(qkv: torch.Tensor, kv_e: torch.Tensor, att: torch.Tensor, n_sent: int) -> torch.Tensor:
+    _need_cuda(qkv, kv_e, att)
+    assert qkv.is_contiguous() and kv_e.is_contiguous() and att.is_contiguous()
+    _check(load().dsc_star_satellite_attn(qkv.data_ptr(), kv_e.data_ptr(), att.data_ptr(), n_sent, _stream()),
+           "dsc_star_satellite_attn")
+    return att
+
+
+def star_relay_attn(qkv_r: torch.Tensor, kv2: Optional[torch.Tensor], n2: int, out: torch.Tensor, n_sent: int):
+    _need_cuda(qkv_r, kv2, out)
+    kv2_rows = 0 if kv2 is None else kv2.shape[1]
+    if kv2 is not None:
+        assert kv2.is_contiguous() and kv2.shape[2] == 256
+    _check(load().dsc_star_relay_attn(qkv_r.data_ptr(), _ptr(kv2), kv2_rows, n2, out.data_ptr(), n_sent, _stream()),
+           "dsc_star_relay_attn")
+    return out
+
+
+def mha_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor,
+                  mask: Optional[torch.Tensor] = None, key_ids: Optional[torch.Tensor] = None,
+                  causal: bool = False, q_off: int = 0) -> torch.Tensor:
+    """q [n, lq, 128], k/v [n, lk, 128] (views with free row/batch strides, k and v sharing strides);
+    mask broadcastable to [n, 1, lq, lk] float 0/1; key_ids [n, >=lk] int32."""
+    _need_cuda(q, k, v, out, mask, key_ids)
+    n, lq, _ = q.shape
+    lk = k.shape[1]
+    assert k.stride() == v.stride() and q.stride(2) == 1 and k.stride(2) == 1 and out.stride(2) == 1
+    mb = mq = 0
+    mptr = None
+    if mask is not None:
+        m = _f32(mask)
+        if m.dim() == 2:
+            m = m[None, None]
+        m = m.broadcast_to((n, 1, lq, lk))
+        if m.stride(3) != 1 and lk > 1:
+            m = m.contiguous()
+        mb, mq, mptr = m.stride(0), m.stride(2), m.data_ptr()
+        mask = m  # keep alive
+    kis = 0
+    if key_ids is not None:
+        assert key_ids.dtype == torch.int32 and key_ids.shape[0] == n and key_ids.shape[1] >= lk
+        assert key_ids.shape[1] == 1 or key_ids.stride(1) == 1
+        kis = key_ids.stride(0)
+    _check(load().dsc_mha_attention(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(1),
+                                    k.stride(0), out.data_ptr(), out.stride(1), out.stride(0), mptr, mb, mq,
+                                    _ptr(key_ids), kis, int(causal), q_off, n, lq, lk, _stream()),
+           "dsc_mha_attention")
+    return out
+
+
+def unit_sumsq(x: torch.Tensor, n_units: int) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.is_contiguous() and x.numel() % n_units == 0
+    out = torch.empty((n_units,), device=x.device, dtype=torch.float32)
+    _check(load().dsc_unit_sumsq(_f32(x).data_ptr(), out.data_ptr(), n_units, x.numel() // n_units, _stream()),
+           "dsc_unit_sumsq")
+    return out
+
+
+def power_normalize(x: torch.Tensor, n_units: int, factor: float = 1.0, sumsq: Optional[torch.Tensor] = None):
+    """x / sqrt(factor * mean(x^2)) per unit (contiguous x split evenly into n_units)."""
+    _need_cuda(x, sumsq)
+    assert x.is_contiguous()
+    if sumsq is None:
+        sumsq = unit_sumsq(x, n_units)
+    out = torch.empty_like(x)
+    _check(load().dsc_power_normalize(_f32(x).data_ptr(), sumsq.data_ptr(), factor, out.data_ptr(), n_units,
+                                      x.numel() // max(n_units, 1), _stream()), "dsc_power_normalize")
+    return out
+
+
+def channel(x: torch.Tensor, n_units: int, n_std: torch.Tensor, *, x_sumsq=None, x_factor: float = 1.0,
+            noise=None, seed: int = 0, offset: int = 0, p=None, p_sumsq=None, p_factor: float = 1.0,
+            p_scale=None, h=None, detector: int = 0, want_x_norm: bool = False):
+    """The fused channel kernel; returns (y, x_norm or None)."""
+    _need_cuda(x, n_std, x_sumsq, noise, p, p_sumsq, p_scale, h)
+    assert x.is_contiguous() and x.numel() % max(n_units, 1) == 0
+    for t in (noise, p):
+        assert t is None or (t.is_contiguous() and t.numel() == x.numel())
+    assert n_std.numel() == n_units and (h is None or (h.is_contiguous() and h.numel() == 2 * n_units))
+    y = torch.empty_like(x)
+    xn = torch.empty_like(x) if want_x_norm else None
+    _check(load().dsc_channel(_f32(x).data_ptr(), _ptr(x_sumsq), x_factor, _ptr(noise), seed, offset, _ptr(p),
+                              _ptr(p_sumsq), p_factor, _ptr(p_scale), _ptr(h), _f32(n_std).data_ptr(), detector,
+                              y.data_ptr(), _ptr(xn), n_units, x.numel() // max(n_units, 1), _stream()),
+           "dsc_channel")
+    return y, xn
+
+
+def vocab_argmax(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n_vocab: int, ids_out: torch.Tensor,
+                 logits: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
+                 prec: int = 0) -> torch.Tensor:
+    """ids_out [M] int32 view (any stride) <- argmax(x @ w[:, :n_vocab] + bias)."""
+    _need_cuda(x, w, bias, ids_out, logits, workspace)
+    M = x.shape[0]
+    assert x.dim() == 2 and x.shape[1] == 128 and x.stride(1) == 1 and ids_out.dtype == torch.int32
+    assert ids_out.dim() == 1 and ids_out.shape[0] == M
+    ld_logits = 0
+    if logits is not None:
+        assert logits.dim() == 2 and logits.shape == (M, n_vocab) and logits.stride(1) == 1
+        ld_logits = logits.stride(0)
+    elif workspace is None:
+        workspace = torch.empty((load().dsc_vocab_argmax_workspace(M, n_vocab),), device=x.device,
+                                dtype=torch.float32)
+    _check(load().dsc_vocab_argmax(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), bias.data_ptr(),
+                                   ids_out.data_ptr(), ids_out.stride(0) if M > 1 else 1, _ptr(logits), ld_logits,
+                                   _ptr(workspace), 0 if workspace is None else workspace.numel(),
+                                   M, n_vocab, prec, _stream()), "dsc_vocab_argmax")
+    return ids_out
+
+
+def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
+    """[..., N] float32 (last dim contiguous, uniform row stride) -> [...] int32."""
+    _need_cuda(logits)
+    N = logits.shape[-1]
+    flat = logits.reshape(-1, N)
+    ids = torch.empty((flat.shape[0],), device=logits.device, dtype=torch.int32)
+    _check(load().dsc_argmax_rows(_f32(flat).data_ptr(), flat.stride(0), ids.data_ptr(), 1, flat.shape[0], N,
+                                  _stream()), "dsc_argmax_rows")
+    return ids.reshape(logits.shape[:-1])
+
+
+def masked_ce_rows(logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    _need_cuda(logits, target)
+    N = logits.shape[-1]
+    flat = logits.reshape(-1, N)
+    tgt = target.reshape(-1).to(torch.int32).contiguous()
+    assert tgt.numel() == flat.shape[0]
+    out = torch.empty((flat.shape[0],), device=logits.device, dtype=torch.float32)
+    _check(load().dsc_masked_ce_rows(_f32(flat).data_ptr(), flat.stride(0), tgt.data_ptr(), out.data_ptr(),
+                                     flat.shape[0], N, _stream()), "dsc_masked_ce_rows")
+    return out.reshape(target.shape)
+
+
+def bleu_counts(ref: torch.Tensor, hyp: torch.Tensor) -> torch.Tensor:
+    """ref [n, Lr], hyp [n, Lh] int32 contiguous -> counts [n, 10] int32."""
+    _need_cuda(ref, hyp)
+    assert ref.dtype == torch.int32 and hyp.dtype == torch.int32 and ref.is_contiguous() and hyp.is_contiguous()
+    n = ref.shape[0]
+    out = torch.empty((n, 10), device=ref.device, dtype=torch.int32)
+    _check(load().dsc_bleu_counts(ref.data_ptr(), ref.shape[1], hyp.data_ptr(), hyp.shape[1], out.data_ptr(), n,
+                                  _stream()), "dsc_bleu_counts")
+    return out
+
+
+def fgm_normalize(g: torch.Tensor, n_units: int, epsilon: float = 1.0) -> torch.Tensor:
+    """g [n_units*samples, ...] contiguous float32 -> p of the same shape."""
+    _need_cuda(g)
+    assert g.is_contiguous() and g.shape[0] % n_units == 0
+    samples = g.shape[0] // n_units
+    p = torch.empty_like(g)
+    _check(load().dsc_fgm_normalize(_f32(g).data_ptr(), p.data_ptr(), float(epsilon), n_units, samples,
+                                    g.numel() // g.shape[0], _stream()), "dsc_fgm_normalize")
+    return p

@@ -1,0 +1,165 @@
+"""Batched transmit + greedy decode over many 64-sentence units in one set of launches.
+
+This is the device-side body of the reference's ``greedy_decode_noattack`` (utlis/eval.py:78-117),
+restructured for throughput without changing a result:
+
+* many units per launch; the per-unit scalars (power norm, noise std, fading coefficient) are indexed
+  per unit inside the fused channel kernel, so a unit is never split;
+* loop invariants hoisted out of the 30 steps (the reference recomputes the channel decoder every
+  step, :106);
+* rows that cannot change are cached: with a causal mask, row i of ``multi_tar`` / the baseline decoder
+  depends only on the prefix, so each step only computes the newest row (k|v caches);
+* only memory position 30 (star decoders, D11) / the newest position (baseline) goes through the
+  layer norms and the vocabulary projection, and logits are reduced to ids on the fly.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .models import modules as M
+from .models.modules import StarWorkspace, star_cycles, _add_ln
+
+START_IDX = 1
+
+
+def transmit(net, inp: torch.Tensor, n_units: int, n_std: torch.Tensor, *, channel: str = "AWGN",
+             noise: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
+             h: Optional[torch.Tensor] = None, p: Optional[torch.Tensor] = None,
+             p_scale: Optional[torch.Tensor] = None, detector: int = 0):
+    """inp [S,31] int32 -> (raw symbols [S,31,16], received symbols [S,31,16]).  Encoder + channel
+    encoder + fused power-norm/channel.  n_std [n_units]; h [n_units,2] for fading; p/p_scale for AWGN."""
+    enc_mask = M.create_padding_mask(inp)
+    sem = net.semantic_encoder.call(inp, False, enc_mask)
+    u = net.channel_encoder.raw(sem).contiguous()
+    sumsq = _lib.unit_sumsq(u, n_units)
+    if channel != "AWGN" and h is None:
+        raise ValueError("fading channels need the per-unit coefficients h [n_units, 2]")
+    y, _ = _lib.channel(u, n_units, n_std, x_sumsq=sumsq, x_factor=1.0, noise=noise, seed=seed, offset=offset,
+                        p=p, p_scale=p_scale, h=h if channel != "AWGN" else None, detector=detector)
+    return u, y
+
+
+class _StarLayerState:
+    def __init__(self, layer, relay, ln_a, ln_b, n_sent, max_len, device):
+        f = dict(device=device, dtype=torch.float32)
+        self.layer, self.relay, self.ln_a, self.ln_b = layer, relay, ln_a, ln_b
+        self.kv_tar = torch.empty((n_sent, max_len, 256), **f)   # k|v of tar rows under multi_tar
+        self.kv2 = torch.empty((n_sent, max_len, 256), **f)      # k|v of h2 rows under the relay weights
+        self.ws = StarWorkspace(n_sent, device)
+        self.tile = torch.empty((n_sent, 32, 128), **f)
+
+
+class StarGreedyDecoder:
+    """Greedy decode for ``Transeiver_Star`` (SD/STD) and ``Transeiver_star`` (SDecoder)."""
+
+    def __init__(self, net, n_sent: int, max_length: int = 30):
+        dec = net.semantic_decoder
+        dev = dec.embedding.embeddings.device
+        self.net, self.dec, self.n, self.max_length, self.dev = net, dec, n_sent, max_length, dev
+        if isinstance(dec, M.SD):
+            L = dec.dec_layers
+            self.layers = [_StarLayerState(L, L.multi_att_relay, L.layernorm2, L.layernorm3, n_sent, max_length, dev)]
+        else:
+            self.layers = [_StarLayerState(L, L.multi_att_satellite, L.layernorm1, L.layernorm2, n_sent, max_length, dev)
+                           for L in dec.dec_layers]
+        self.outputs = torch.zeros((n_sent, max_length + 1), device=dev, dtype=torch.int32)
+        self.last = torch.empty((n_sent, 1, 128), device=dev, dtype=torch.float32)
+        self.mid = torch.empty((n_sent, 31, 128), device=dev, dtype=torch.float32)
+        self.vocab = dec.final_layer.kernel.shape[1]
+        self.logit_ws = torch.empty((_lib.load().dsc_vocab_argmax_workspace(n_sent, self.vocab),), device=dev,
+                                    dtype=torch.float32)
+
+    def decode(self, received: torch.Tensor, start_idx: int = START_IDX) -> torch.Tensor:
+        net, dec, S = self.net, self.dec, self.n
+        mem = net.channel_decoder.call(received)                      # hoisted out of the step loop
+        st0 = self.layers[0]
+        _lib.star_pack(mem.contiguous(), st0.tile)
+        _lib.linear(st0.tile.view(S * 32, 128), st0.layer.multi_att_satellite._packed("kv"), None, out=st0.ws.kv_e,
+                    prec=M.PREC)
+        self.outputs.zero_()
+        self.outputs[:, 0] = start_idx
+        wf, bf = dec.final_layer.padded_kernel(), dec.final_layer.bias.detach()
+        for t in range(self.max_length):
+            x_t = dec._embed(self.outputs[:, t:t + 1], pos0=t)        # [S,1,128]
+            x2 = x_t.view(S, 128)
+            for li, st in enumerate(self.layers):
+                L = st.layer
+                q_t = L.multi_tar.wq(x2).view(S, 1, 128)
+                _lib.linear(x2, L.multi_tar._packed("kv"), None, out=st.kv_tar[:, t, :], prec=M.PREC)
+                a = L.multi_tar.attend(q_t, st.kv_tar[:, :t + 1, 0:128], st.kv_tar[:, :t + 1, 128:256],
+                                       key_ids=self.outputs)           # causal: the newest row sees the whole prefix
+                h2_t = _add_ln(a, x_t, L.layernorm1)
+                _lib.linear(h2_t.view(S, 128), st.relay._packed("kv"), None, out=st.kv2[:, t, :], prec=M.PREC)
+                if li > 0:                                             # memory of layer li = output of layer li-1
+                    _lib.star_pack(self.mid, st.tile)
+                x = star_cycles(st.tile, L.multi_att_satellite, st.relay, L.cycle_num, st.kv2, t + 1, st.ws,
+                                kv_e_ready=(li == 0))
+                if li + 1 < len(self.layers):
+                    _add_ln(x[:, :31], st.tile[:, :31], st.ln_a, st.ln_b, out=self.mid)
+                else:
+                    _add_ln(x[:, 30:31], st.tile[:, 30:31], st.ln_a, st.ln_b, out=self.last)
+            _lib.vocab_argmax(self.last.view(S, 128), wf, bf, self.vocab, self.outputs[:, t + 1],
+                              workspace=self.logit_ws, prec=M.PREC)
+        return self.outputs
+
+
+class BaselineGreedyDecoder:
+    """Greedy decode for ``Transeiver`` / ``Transeiver_GAN`` (Decoder with self-attention k|v caches and
+    per-layer cross-attention k|v of the memory computed once)."""
+
+    def __init__(self, net, n_sent: int, max_length: int = 30):
+        dec = net.semantic_decoder
+        dev = dec.embedding.embeddings.device
+        f = dict(device=dev, dtype=torch.float32)
+        self.net, self.dec, self.n, self.max_length = net, dec, n_sent, max_length
+        self.kv_self = [torch.empty((n_sent, max_length, 256), **f) for _ in dec.dec_layers]
+        self.kv_cross = [torch.empty((n_sent, 31, 256), **f) for _ in dec.dec_layers]
+        self.outputs = torch.zeros((n_sent, max_length + 1), device=dev, dtype=torch.int32)
+        self.vocab = dec.final_layer.kernel.shape[1]
+        self.logit_ws = torch.empty((_lib.load().dsc_vocab_argmax_workspace(n_sent, self.vocab),), **f)
+
+    def decode(self, received: torch.Tensor, inp: torch.Tensor, start_idx: int = START_IDX) -> torch.Tensor:
+        net, dec, S = self.net, self.dec, self.n
+        mem = net.channel_decoder.call(received).contiguous()
+        for L, kvc in zip(dec.dec_layers, self.kv_cross):
+            _lib.linear(mem.view(S * 31, 128), L.sl12._packed("kv"), None, out=kvc.view(S * 31, 256), prec=M.PREC)
+        self.outputs.zero_()
+        self.outputs[:, 0] = start_idx
+        wf, bf = dec.final_layer.padded_kernel(), dec.final_layer.bias.detach()
+        for t in range(self.max_length):
+            x = dec._embed(self.outputs[:, t:t + 1], pos0=t)          # [S,1,128]
+            for L, kvs, kvc in zip(dec.dec_layers, self.kv_self, self.kv_cross):
+                x2 = x.view(S, 128)
+                q = L.sl11.wq(x2).view(S, 1, 128)
+                _lib.linear(x2, L.sl11._packed("kv"), None, out=kvs[:, t, :], prec=M.PREC)
+                a = L.sl11.attend(q, kvs[:, :t + 1, 0:128], kvs[:, :t + 1, 128:256], key_ids=self.outputs)
+                o1 = _add_ln(a, x, L.layernorm1)
+                q2 = L.sl12.wq(o1.view(S, 128)).view(S, 1, 128)
+                a2 = L.sl12.attend(q2, kvc[:, :, 0:128], kvc[:, :, 128:256], key_ids=inp)
+                x = _add_ln(a2, o1, L.layernorm2, L.layernorm3)
+            _lib.vocab_argmax(x.view(S, 128), wf, bf, self.vocab, self.outputs[:, t + 1], workspace=self.logit_ws,
+                              prec=M.PREC)
+        return self.outputs
+
+
+def make_decoder(net, n_sent: int, max_length: int = 30):
+    if isinstance(net.semantic_decoder, (M.SD, M.SDecoder)):
+        return StarGreedyDecoder(net, n_sent, max_length)
+    return BaselineGreedyDecoder(net, n_sent, max_length)
+
+
+def greedy_units(net, inp: torch.Tensor, n_units: int, n_std: torch.Tensor, *, channel: str = "AWGN",
+                 noise=None, seed: int = 0, offset: int = 0, h=None, p=None, p_scale=None, detector: int = 0,
+                 max_length: int = 30, start_idx: int = START_IDX, decoder=None) -> torch.Tensor:
+    """Transmit + greedy decode for ``n_units`` units stacked along the batch axis.  Returns ids [S, 31]."""
+    inp = inp.to(torch.int32).contiguous()
+    _, y = transmit(net, inp, n_units, n_std, channel=channel, noise=noise, seed=seed, offset=offset, h=h, p=p,
+                    p_scale=p_scale, detector=detector)
+    if decoder is None:
+        decoder = make_decoder(net, inp.shape[0], max_length)
+    if isinstance(decoder, StarGreedyDecoder):
+        return decoder.decode(y, start_idx)
+    return decoder.decode(y, inp, start_idx)

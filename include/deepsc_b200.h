@@ -1,0 +1,158 @@
+/*
+ * deepsc_b200.h - C ABI of libdeepsc_b200.so, the sm_100a implementation of the
+ * DeepSC-GAN transmit path (encode -> channel(+attack) -> decode -> BLEU).
+ *
+ * The reference (jiang99999/DeepSC-GAN) is TensorFlow/Keras Python with no FFI of
+ * its own; its seam is the Keras layer call.  Each entry point below replaces the
+ * library ops behind one reference call site (cited as DeepSC-GAN/<file>:<line>);
+ * INTEGRATION.md shows the ctypes stub a maintainer would bind them with.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer (caller-owned; the library never allocates,
+ *    frees or retains pointers past the call); fp32 row-major unless stated;
+ *  - `ld*` are leading dimensions in elements; rows of 128 floats must be 16-byte aligned;
+ *  - `stream` is a cudaStream_t; every call is asynchronous on it and re-entrant;
+ *  - return 0 on success, a negative dsc_status otherwise; dsc_last_error() gives the
+ *    thread-local message.  Nothing throws across the ABI.  There is no CPU fallback.
+ *  - the "star tile" layout is [sentences][32][128]: rows 0..30 are the satellite nodes
+ *    (tokens, sequence length is fixed at 31, dataset/dataloader.py:11) and row 31 is the
+ *    relay node s.
+ */
+#ifndef DEEPSC_B200_H
+#define DEEPSC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSC_D_MODEL 128
+#define DSC_HEADS 8
+#define DSC_SEQ 31        /* satellites per sentence */
+#define DSC_TILE_ROWS 32  /* satellites + relay */
+#define DSC_SYMS 16       /* channel uses per token */
+
+typedef enum {
+  DSC_OK = 0,
+  DSC_ERR_BAD_ARG = -1,    /* null pointer, bad size, misaligned leading dimension */
+  DSC_ERR_CUDA = -2,       /* launch or runtime error; message holds cudaGetErrorString */
+  DSC_ERR_UNSUPPORTED = -3 /* shape outside what the kernels are written for */
+} dsc_status;
+
+/* library identity ------------------------------------------------------------------ */
+int dsc_version(void);               /* 10000*major + 100*minor + patch */
+const char* dsc_last_error(void);    /* thread-local, never NULL */
+int dsc_device_arch(void);           /* 10*major + minor of the current device, or <0 */
+
+/* K1: embedding gather * sqrt(128) + positional row.
+ * replaces Embedding + scale + pos_encoding, models/modules.py:497-502, 542-544, 661-666, 706-708.
+ * ids are read at ids[s*ids_stride + i], i < len; token i of sentence s gets position pos0+i;
+ * out row (s*len + i) has leading dimension ld_out. */
+int dsc_embed(const int32_t* ids, int64_t ids_stride, const float* table, int vocab,
+              const float* pos_table, float* out, int64_t ld_out,
+              int n_sent, int len, int pos0, void* stream);
+
+/* K2/K7/K10/K11/K12: y = act(x @ w + bias), the tf.keras.layers.Dense call
+ * (models/modules.py:35-39,110-121,536; models/transceiver.py:89-90,103-105; models/gan.py:7-8).
+ * w is Keras layout [K, N] with leading dimension ldw (ldw % 4 == 0, columns [N,ldw) readable).
+ * act: 0 none, 1 relu.  If row_mod > 0, rows with (row % row_mod) == row_skip are not stored.
+ * prec: 0 = fp32 FFMA kernel; 1 = tcgen05 bf16x3 split (fp32-class accuracy); 2 = tcgen05 bf16. */
+int dsc_linear(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+               float* y, int64_t ldy, int M, int K, int N, int act,
+               int row_mod, int row_skip, int prec, void* stream);
+
+/* K6: out = LN_b(2 * LN_a(x + res)) (gamma_b != NULL) or LN_a(x + res); eps = 1e-6, biased variance.
+ * replaces LayerNormalization call sites models/modules.py:310-314, 354, 382-386, 425-429, 458-467;
+ * models/transceiver.py:112.  Rows are addressed in groups: logical row r -> group r / group_rows,
+ * member r % group_rows, element offset group*<x|res|out>_group_stride + member*128. */
+int dsc_add_layernorm(const float* x, int64_t x_group_stride, const float* res, int64_t res_group_stride,
+                      const float* gamma_a, const float* beta_a, const float* gamma_b, const float* beta_b,
+                      float* out, int64_t out_group_stride, int n_rows, int group_rows, void* stream);
+
+/* star tile helpers: pack [n_sent,31,128] into the tile layout and set row 31 = mean over the
+ * 31 rows (s = reduce_mean(h, axis=1), models/modules.py:286,359). */
+int dsc_star_pack(const float* src, float* tile, int n_sent, void* stream);
+
+/* K3: satellite attention of one star cycle (models/modules.py:289-299, 361-372), deduplicated:
+ * qkv  [n_sent*32, 384] = tile @ [wq|wk|wv] of multi_att_satellite (row 31 carries k_s, v_s);
+ * kv_e [n_sent*32, 256] = e-tile @ [wk|wv] (constant over cycles);
+ * att  [n_sent*32, 128]: rows 0..30 = sum_j softmax_j(q.k_j/4) v_j over the five keys
+ * {h[i+1], h[i], h[i-1], e[i], s} (cyclic neighbours, no mask); row 31 is zero-filled. */
+int dsc_star_satellite_attn(const float* qkv, const float* kv_e, float* att, int n_sent, void* stream);
+
+/* K4: relay attention of one star cycle (models/modules.py:303-306, 375-378).
+ * qkv_r [n_sent*32, 384] = updated tile @ [wq|wk|wv] of the relay weights; the query is row 31,
+ * keys/values are row 31 (s), rows 0..30 (h) and, for the decoder, the first n2 rows of
+ * kv2 [n_sent, kv2_rows, 256] (k|v of h2 under the relay weights).  out [n_sent, 128]. */
+int dsc_star_relay_attn(const float* qkv_r, const float* kv2, int kv2_rows, int n2,
+                        float* out, int n_sent, void* stream);
+
+/* K5: softmax(q k^T / 4 + mask * -1e9) v for 8 heads of depth 16 (sublayer1.scale_dot_product_attention,
+ * models/modules.py:41-76).  q [n, lq, 128] (ldq between rows, q_batch_stride between sentences),
+ * k,v [n, lk, 128] likewise.  Masking is the sum of: a dense 0/1 float mask read at
+ * mask[b*mask_b_stride + i*mask_q_stride + j] (NULL = none), key_ids (NULL = none) masking
+ * keys whose id is 0 (create_padding_mask :757), and causal != 0 masking j > q_off + i
+ * (create_look_ahead_mask :761).  lq <= 64, lk <= 64. */
+int dsc_mha_attention(const float* q, int64_t ldq, int64_t q_batch_stride,
+                      const float* k, const float* v, int64_t ldkv, int64_t kv_batch_stride,
+                      float* out, int64_t ldo, int64_t o_batch_stride,
+                      const float* mask, int64_t mask_b_stride, int64_t mask_q_stride,
+                      const int32_t* key_ids, int64_t key_ids_stride, int causal, int q_off,
+                      int n, int lq, int lk, void* stream);
+
+/* K8: per-unit sum of squares; unit u covers elems_per_unit consecutive floats
+ * (the whole-batch reduce_mean(x^2) of models/transceiver.py:91 and models/gan.py:9). */
+int dsc_unit_sumsq(const float* x, float* sumsq, int n_units, int64_t elems_per_unit, void* stream);
+
+/* K8: out = x / sqrt(factor * sumsq[u] / elems_per_unit): the power-norm Lambda of
+ * models/transceiver.py:91 (factor 1) and models/gan.py:9 (factor 2). */
+int dsc_power_normalize(const float* x, const float* sumsq, float factor, float* out,
+                        int n_units, int64_t elems_per_unit, void* stream);
+
+/* K9: the fused channel (models/transceiver.py:25-33 awgn, :35-83 fading; utlis/eval.py:90-93).
+ * For element e of unit u (elems_per_unit floats, adjacent pairs are I/Q):
+ *   xs = x / sqrt(x_factor * x_sumsq[u] / elems_per_unit)        (x_sumsq NULL: xs = x)
+ *   z  = noise[e] (unit normal) or Philox4x32-10 + Box-Muller(seed, e)  (noise NULL)
+ *   ps = p[e] * p_scale[u] / sqrt(p_factor * p_sumsq[u] / elems_per_unit)   (p NULL: 0; p_sumsq NULL: no divide)
+ *   AWGN   (h NULL): y = xs + n_std[u]*z + ps
+ *   fading (h[u] = (re, im)): y = xs*h + n_std[u]*z  (complex); detector 1 = LS  y*conj(h)/|h|^2,
+ *                             2 = MMSE y*conj(h)/(|h|^2 + 2 n_std^2), 0 = return y (reference :74-75)
+ * xs is also written to x_norm when x_norm != NULL (Channel_Encoder's return value). */
+int dsc_channel(const float* x, const float* x_sumsq, float x_factor,
+                const float* noise, uint64_t seed, uint64_t offset,
+                const float* p, const float* p_sumsq, float p_factor, const float* p_scale,
+                const float* h, const float* n_std, int detector,
+                float* y, float* x_norm, int n_units, int64_t elems_per_unit, void* stream);
+
+/* K12+K13: ids[r*ids_stride] = argmax_j (x[r] . w[:, j] + bias[j]), j < N, smallest index among ties
+ * (tf.argmax, utlis/eval.py:112-113).  Logits are not materialised unless logits != NULL
+ * (then logits[r*ld_logits + j] is stored as well, the `predictions` tensor of Transeiver*.call). */
+int dsc_vocab_argmax(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                     int32_t* ids, int64_t ids_stride, float* logits, int64_t ld_logits,
+                     float* workspace, int64_t workspace_floats,
+                     int M, int N, int prec, void* stream);
+int64_t dsc_vocab_argmax_workspace(int M, int N);   /* floats */
+
+/* K13 standalone: row-wise argmax of materialised logits. */
+int dsc_argmax_rows(const float* logits, int64_t ld, int32_t* ids, int64_t ids_stride, int M, int N, void* stream);
+
+/* K14: masked sparse CE (loss_function, models/modules.py:738-755): per-row
+ * (logsumexp(logits[r]) - logits[r][target[r]]) * (target[r] != 0) into row_loss[r]. */
+int dsc_masked_ce_rows(const float* logits, int64_t ld, const int32_t* target, float* row_loss,
+                       int M, int N, void* stream);
+
+/* K16: BLEU n-gram counts (utlis/tools.py:15-24,37-43 restated on ids).
+ * ref [n, ref_len], hyp [n, hyp_len] int32; counts [n,10] = match_1..4, total_1..4, hyp_len, ref_len. */
+int dsc_bleu_counts(const int32_t* ref, int ref_len, const int32_t* hyp, int hyp_len,
+                    int32_t* counts, int n, void* stream);
+
+/* K15: FGM normalisation (utlis/eval.py:215-224): p = r/||r||_F with r_b = eps*g_b/||g_b||_2 per
+ * sample of a unit; g [n_units, samples_per_unit, elems_per_sample]. */
+int dsc_fgm_normalize(const float* g, float* p, float epsilon, int n_units, int samples_per_unit,
+                      int elems_per_sample, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPSC_B200_H */

@@ -1,0 +1,42 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/deepsc_b200.h declares."""
+import ctypes
+import os
+import re
+
+import deepsc_gan_b200  # noqa: F401
+from deepsc_gan_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "deepsc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dsc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in deepsc_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), "ctypes prototypes out of sync with the header"
+
+
+def test_version_and_error_channel():
+    lib = _lib.load()
+    assert lib.dsc_version() >= 100
+    assert isinstance(lib.dsc_last_error(), bytes)
+    # argument validation happens before any CUDA call, so it can be exercised without a GPU
+    rc = lib.dsc_linear(None, 128, None, 128, None, None, 128, 4, 128, 128, 0, 0, 0, 0, None)
+    assert rc == -1 and b"null pointer" in lib.dsc_last_error()
+    rc = lib.dsc_channel(16, None, 1.0, None, 0, 0, None, None, 1.0, None, None, 16, 7, 16, None, 1, 64, None)
+    assert rc == -1 and lib.dsc_last_error() == b"detector must in LS and MMSE"
+
+
+def test_product_has_no_cpu_fallback():
+    import pytest
+    import torch
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.unit_sumsq(torch.zeros(64), 1)
