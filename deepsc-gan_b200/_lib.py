@@ -25,6 +25,9 @@ _SIGNATURES = {
     "dsc_device_arch": (C.c_int, []),
     "dsc_embed": (C.c_int, [vp, i64, vp, i32, vp, vp, i64, i32, i32, i32, vp]),
     "dsc_linear": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
+    "dsc_packed_weight_bytes": (C.c_int64, [i32, i32]),
+    "dsc_pack_weight": (C.c_int, [vp, i64, i32, i32, vp, vp]),
+    "dsc_linear_tc": (C.c_int, [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, i32, vp]),
     "dsc_add_layernorm": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "dsc_star_pack": (C.c_int, [vp, vp, i32, vp]),
     "dsc_star_satellite_attn": (C.c_int, [vp, vp, vp, i32, vp]),
@@ -119,6 +122,26 @@ def embed(ids: torch.Tensor, table: torch.Tensor, pos_table: torch.Tensor, pos0:
     return out
 
 
+_PACK_CACHE = {}
+
+
+def packed_weight(w: torch.Tensor, n: int) -> torch.Tensor:
+    """bf16 hi/lo UMMA image of a Keras-layout weight (cached per storage + version)."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.stride(0), n, w.device.index)
+    hit = _PACK_CACHE.get(key)
+    if hit is None:
+        K = w.shape[0]
+        nbytes = load().dsc_packed_weight_bytes(K, n)
+        blob = torch.empty((nbytes,), device=w.device, dtype=torch.uint8)
+        _check(load().dsc_pack_weight(_f32(w).data_ptr(), w.stride(0), K, n, blob.data_ptr(), _stream()),
+               "dsc_pack_weight")
+        if len(_PACK_CACHE) > 256:
+            _PACK_CACHE.clear()
+        hit = (blob, w)          # keep the source alive so its data_ptr cannot be recycled under the key
+        _PACK_CACHE[key] = hit
+    return hit[0]
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0,
            out: Optional[torch.Tensor] = None, n: Optional[int] = None, row_mod: int = 0, row_skip: int = 0,
            prec: int = 0) -> torch.Tensor:
@@ -133,9 +156,14 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     if PROFILE is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    _check(load().dsc_linear(_f32(x).data_ptr(), x.stride(0), _f32(w).data_ptr(), w.stride(0), _ptr(bias),
-                             out.data_ptr(), out.stride(0), M, K, N, act, row_mod, row_skip, prec, _stream()),
-           "dsc_linear")
+    if prec != 0 and K % 128 == 0:
+        blob = packed_weight(w, N)
+        _check(load().dsc_linear_tc(_f32(x).data_ptr(), x.stride(0), blob.data_ptr(), _ptr(bias), out.data_ptr(),
+                                    out.stride(0), M, K, N, act, row_mod, row_skip, prec, _stream()), "dsc_linear_tc")
+    else:
+        _check(load().dsc_linear(_f32(x).data_ptr(), x.stride(0), _f32(w).data_ptr(), w.stride(0), _ptr(bias),
+                                 out.data_ptr(), out.stride(0), M, K, N, act, row_mod, row_skip, 0, _stream()),
+               "dsc_linear")
     if PROFILE is not None:
         ev1.record()
         PROFILE.append((ev0, ev1, M, K, N))

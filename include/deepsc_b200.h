@@ -62,6 +62,17 @@ int dsc_linear(const float* x, int64_t ldx, const float* w, int64_t ldw, const f
                float* y, int64_t ldy, int M, int K, int N, int act,
                int row_mod, int row_skip, int prec, void* stream);
 
+/* tcgen05 Dense path.  dsc_pack_weight splits a Keras-layout fp32 weight [K, N] into bf16 hi/lo planes laid
+ * out as the K-major, 128-byte-swizzled shared-memory image the UMMA descriptors expect
+ * (dsc_packed_weight_bytes(K, N) bytes, 128-byte aligned, K % 64 == 0); the caller owns and caches the blob.
+ * dsc_linear_tc is dsc_linear on those planes: prec 1 = three bf16 passes (x_hi*W_hi + x_lo*W_hi + x_hi*W_lo,
+ * fp32 accumulation in TMEM), prec 2 = one bf16 pass.  K % 128 == 0. */
+int64_t dsc_packed_weight_bytes(int K, int N);
+int dsc_pack_weight(const float* w, int64_t ldw, int K, int N, void* blob, void* stream);
+int dsc_linear_tc(const float* x, int64_t ldx, const void* packed_w, const float* bias,
+                  float* y, int64_t ldy, int M, int K, int N, int act,
+                  int row_mod, int row_skip, int prec, void* stream);
+
 /* K6: out = LN_b(2 * LN_a(x + res)) (gamma_b != NULL) or LN_a(x + res); eps = 1e-6, biased variance.
  * replaces LayerNormalization call sites models/modules.py:310-314, 354, 382-386, 425-429, 458-467;
  * models/transceiver.py:112.  Rows are addressed in groups: logical row r -> group r / group_rows,

@@ -295,3 +295,38 @@ def test_bad_arguments_raise(L, dev):
         L.linear(torch.zeros(4, 24, device=dev), torch.zeros(24, 16, device=dev), None)
     with pytest.raises(ValueError):
         L.bleu_counts(torch.zeros(2, 40, dtype=torch.int32, device=dev), torch.zeros(2, 40, dtype=torch.int32, device=dev))
+
+
+@pytest.mark.parametrize("prec,tol", [(1, 3e-5), (2, 2e-2)])
+@pytest.mark.parametrize("M,K,N,act", [(128, 128, 128, 0), (1984, 128, 384, 0), (300, 128, 256, 1), (64, 128, 22234, 0),
+                                       (257, 512, 128, 1), (200, 256, 16, 0)])
+def test_linear_tensor_core(L, dev, M, K, N, act, prec, tol):
+    """tcgen05 path: bf16x3 split must be fp32-class (<= 3e-5 relative), single bf16 pass ~1e-2."""
+    g = torch.Generator().manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) / np.sqrt(K)
+    b = torch.randn(N, generator=g)
+    ref = x.double() @ w.double() + b.double()
+    if act:
+        ref = torch.relu(ref)
+    ldw = (N + 127) // 128 * 128
+    wd = torch.zeros(K, ldw, device=dev)
+    wd[:, :N] = w.to(dev)
+    y = torch.full((M, N), 123.0, device=dev)
+    L.linear(x.to(dev), wd, b.to(dev), act=act, n=N, prec=prec, out=y)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) < tol
+
+
+def test_linear_tensor_core_row_skip_strided(L, dev):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(128, 128, generator=g).to(dev)
+    w = torch.randn(128, 128, generator=g).to(dev)
+    out = torch.full((128, 128), 7.0, device=dev)
+    L.linear(x, w, None, out=out, row_mod=32, row_skip=31, prec=1)
+    ref = (x.double() @ w.double()).float()
+    keep = torch.arange(128, device=dev) % 32 != 31
+    assert rel_err(out[keep], ref[keep]) < 3e-5 and bool((out[~keep] == 7.0).all())
+    tile = torch.zeros((4, 32, 128), device=dev)
+    L.linear(x[:4], w, None, out=tile[:, 31, :], prec=1)
+    assert rel_err(tile[:, 31, :], ref[:4]) < 3e-5 and float(tile[:, :31].abs().max()) == 0.0
