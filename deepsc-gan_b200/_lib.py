@@ -31,6 +31,8 @@ _SIGNATURES = {
     "dsc_add_layernorm": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "dsc_star_pack": (C.c_int, [vp, vp, i32, vp]),
     "dsc_star_satellite_attn": (C.c_int, [vp, vp, vp, i32, vp]),
+    "dsc_star_sat_tc": (C.c_int, [vp, vp, vp, vp, i32, i32, vp]),
+    "dsc_star_mix_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp]),
     "dsc_star_relay_attn": (C.c_int, [vp, vp, i32, i32, vp, i32, vp]),
     "dsc_mha_attention": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,
                                     i32, i32, i32, vp]),
@@ -206,6 +208,33 @@ def star_satellite_attn(qkv: torch.Tensor, kv_e: torch.Tensor, att: torch.Tensor
     return att
 
 
+def star_sat_tc(x_tile: torch.Tensor, kv_e: torch.Tensor, w_grouped: torch.Tensor, att: torch.Tensor, n_sent: int,
+                prec: int) -> torch.Tensor:
+    """Fused projection + satellite attention; w_grouped is the [128,384] head-pair-grouped fp32 weight."""
+    _need_cuda(x_tile, kv_e, w_grouped, att)
+    assert x_tile.is_contiguous() and kv_e.is_contiguous() and att.is_contiguous()
+    blob = packed_weight(w_grouped, 384)
+    _check(load().dsc_star_sat_tc(x_tile.data_ptr(), kv_e.data_ptr(), blob.data_ptr(), att.data_ptr(), n_sent, prec,
+                                  _stream()), "dsc_star_sat_tc")
+    return att
+
+
+def star_mix_tc(att: torch.Tensor, x_tile: torch.Tensor, wo: torch.Tensor, bias_o: torch.Tensor, wkv_relay: torch.Tensor,
+                q_relay: torch.Tensor, kv2: Optional[torch.Tensor], n2: int, att_relay: torch.Tensor, n_sent: int,
+                prec: int) -> torch.Tensor:
+    """Fused Wo dense + relu (in place on x_tile rows 0..30) + relay k|v projection + relay attention."""
+    _need_cuda(att, x_tile, wo, bias_o, wkv_relay, q_relay, kv2, att_relay)
+    assert att.is_contiguous() and x_tile.is_contiguous() and q_relay.is_contiguous() and att_relay.is_contiguous()
+    kv2_rows = 0 if kv2 is None else kv2.shape[1]
+    if kv2 is not None:
+        assert kv2.is_contiguous() and kv2.shape[2] == 256
+    _check(load().dsc_star_mix_tc(att.data_ptr(), x_tile.data_ptr(), packed_weight(wo, 128).data_ptr(),
+                                  packed_weight(wkv_relay, 256).data_ptr(), bias_o.data_ptr(), q_relay.data_ptr(),
+                                  _ptr(kv2), kv2_rows, n2, att_relay.data_ptr(), n_sent, prec, _stream()),
+           "dsc_star_mix_tc")
+    return att_relay
+
+
 def star_relay_attn(qkv_r: torch.Tensor, kv2: Optional[torch.Tensor], n2: int, out: torch.Tensor, n_sent: int):
     _need_cuda(qkv_r, kv2, out)
     kv2_rows = 0 if kv2 is None else kv2.shape[1]
@@ -302,6 +331,14 @@ def vocab_argmax(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n_vocab: 
     elif workspace is None:
         workspace = torch.empty((load().dsc_vocab_argmax_workspace(M, n_vocab),), device=x.device,
                                 dtype=torch.float32)
+    if prec != 0:
+        # tensor-core projection into the (caller-provided) logits/workspace rows, then the row argmax kernel
+        ld = (n_vocab + 3) // 4 * 4
+        lg = logits if logits is not None else workspace[: M * ld].view(M, ld)[:, :n_vocab]
+        linear(x, w, bias, out=lg, n=n_vocab, prec=prec)
+        _check(load().dsc_argmax_rows(lg.data_ptr(), lg.stride(0), ids_out.data_ptr(),
+                                      ids_out.stride(0) if M > 1 else 1, M, n_vocab, _stream()), "dsc_argmax_rows")
+        return ids_out
     _check(load().dsc_vocab_argmax(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), bias.data_ptr(),
                                    ids_out.data_ptr(), ids_out.stride(0) if M > 1 else 1, _ptr(logits), ld_logits,
                                    _ptr(workspace), 0 if workspace is None else workspace.numel(),

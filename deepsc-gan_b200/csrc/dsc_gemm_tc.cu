@@ -163,6 +163,109 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
   if (warp == 0) tmem_dealloc<BN>(tmem_d);
 }
 
+
+// ---------------------------------------------------------------- bring-up: A operand from TMEM (TS mode)
+// Same tile as gemm_tc_kernel but thread t owns row t: it splits its 128 fp32 values into bf16 hi/lo pairs and
+// stores them into its own TMEM lane (tcgen05.st 32x32b), columns [A_HI, A_HI+64) and [A_LO, A_LO+64); column c
+// holds k = 2c (low half) and 2c+1 (high half) unless `swap_halves`.  K = 128 only.
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(128, 1)
+gemm_tc_ts_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ blob, int n_pad,
+                  const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
+                  int M, int N, int act, int swap_halves) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sB = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t B_PLANE = BN * 128;
+  __shared__ __align__(8) uint64_t bar_b, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const size_t g_plane = (size_t)n_pad * 128;
+  if (tid == 0) { mbar_init(&bar_b, 1); mbar_init(&bar_mma, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t A_HI = 256, A_LO = 320;                  // column offsets of the A operand
+  constexpr uint32_t IDESC = idesc_bf16_f32(TC_BM, BN);
+  if (tid == 0) {
+    constexpr int parts = (NPASS == 3) ? 2 : 1;
+    mbar_expect_tx(&bar_b, parts * 2 * B_PLANE);
+    for (int p = 0; p < parts; ++p)
+      for (int kb = 0; kb < 2; ++kb)
+        bulk_g2s(sB + (p * 2 + kb) * B_PLANE, blob + ((size_t)p * 2 + kb) * g_plane + (size_t)n0 * 128, B_PLANE, &bar_b);
+  }
+  {
+    const int gr = m0 + tid;
+    const float4* src = reinterpret_cast<const float4*>(x + (int64_t)gr * ldx);
+    const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c8 = 0; c8 < 8; ++c8) {                       // 8 columns = 16 k values per store
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 v = (gr < M) ? __ldg(src + c8 * 4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (swap_halves) { split2(v.y, v.x, hi[2*q], lo[2*q]); split2(v.w, v.z, hi[2*q+1], lo[2*q+1]); }
+        else             { split2(v.x, v.y, hi[2*q], lo[2*q]); split2(v.z, v.w, hi[2*q+1], lo[2*q+1]); }
+      }
+      tmem_st8(lane_addr + A_HI + c8 * 8, hi);
+      if (NPASS == 3) tmem_st8(lane_addr + A_LO + c8 * 8, lo);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    mbar_wait(&bar_b, 0);
+    tc_fence_after();
+    const uint32_t b_base = smem_u32(sB);
+#pragma unroll
+    for (int pass = 0; pass < NPASS; ++pass) {
+      const uint32_t a_col = (pass == 1) ? A_LO : A_HI;
+      const int pb = (pass == 2) ? 1 : 0;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          uint64_t db = smem_desc_sw128(b_base + (pb * 2 + kb) * B_PLANE + ks * 32);
+          umma_ts(tmem_d, tmem_d + a_col + (kb * 4 + ks) * 8, db, IDESC, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+        }
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int j = 0; j < BN / 32; ++j) {
+    float v[32];
+    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+    tmem_ld_wait();
+    const int c0 = n0 + j * 32;
+    if (row < M)
+      for (int e = 0; e < 32; ++e)
+        if (c0 + e < N) {
+          float t = v[e] + (bias ? __ldg(bias + c0 + e) : 0.f);
+          y[(int64_t)row * ldy + c0 + e] = act ? fmaxf(t, 0.f) : t;
+        }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_d);
+}
+
+template <int BN, int NPASS>
+static int launch_gemm_tc_ts(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y,
+                             int64_t ldy, int M, int N, int act, int swap, cudaStream_t stream) {
+  constexpr size_t smem = 4 * (size_t)BN * 128 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_ts_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("dsc_linear_tc(ts): %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
+  dim3 grid(n_pad / BN, (M + TC_BM - 1) / TC_BM);
+  gemm_tc_ts_kernel<BN, NPASS><<<grid, 128, smem, stream>>>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, swap);
+  return check_launch("dsc_linear_tc(ts)");
+}
+
 template <int BN, int NPASS>
 static int launch_gemm_tc(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y,
                           int64_t ldy, int M, int K, int N, int act, int row_mod, int row_skip, cudaStream_t stream) {
@@ -213,11 +316,18 @@ extern "C" int dsc_linear_tc(const float* x, int64_t ldx, const void* packed_w, 
   DSC_REQUIRE((ldx & 3) == 0 && ldx >= K && aligned16(x), "dsc_linear_tc: x rows must be 16-byte aligned");
   DSC_REQUIRE((reinterpret_cast<uintptr_t>(packed_w) & 127u) == 0, "dsc_linear_tc: packed weights must be 128-byte aligned");
   DSC_REQUIRE(ldy >= N && (act == 0 || act == 1), "dsc_linear_tc: bad ldy/act");
+  const int ts_mode = prec & 16, ts_swap = prec & 32;       // bring-up knobs: A operand staged in TMEM
+  prec &= 15;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_linear_tc: prec must be 1 (bf16x3) or 2 (bf16)");
   if (M == 0) return DSC_OK;
   const int n_pad = (N + 127) / 128 * 128;
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(packed_w);
   cudaStream_t s = as_stream(stream);
+  if (ts_mode) {
+    DSC_REQUIRE(K == 128 && row_mod == 0, "dsc_linear_tc(ts): K must be 128");
+    return prec == 1 ? launch_gemm_tc_ts<128, 3>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, ts_swap, s)
+                     : launch_gemm_tc_ts<128, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, ts_swap, s);
+  }
   const bool wide = (n_pad % 256) == 0;
   if (prec == 1) {
     return wide ? launch_gemm_tc<256, 3>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)

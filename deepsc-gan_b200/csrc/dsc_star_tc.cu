@@ -1,0 +1,467 @@
+// Fused star-cycle phase kernels on tcgen05 (sm_100a): persistent, warp-specialised, weights resident in
+// shared memory, the activation operand staged in tensor memory (TS-mode UMMA), accumulators in TMEM.
+//
+//  star_sat_kernel  (K2+K3): per tile of 4 sentences (128 rows = TMEM lanes; a warp quarter is one sentence,
+//      lane 31 its relay row)  QKV = X @ [Wq|Wk|Wv]_satellite by head pairs (N = 96 per UMMA group, double-
+//      buffered accumulators) -> satellite attention over the five keys {h[i+1], h[i], h[i-1], e[i], s} with
+//      neighbour rows fetched by warp shuffle -> ATT rows (fp32) to HBM.  The [rows,384] QKV tensor of the
+//      unfused path never exists.
+//  star_mix_kernel  (K2+K4): ATT @ Wo_sat + b, ReLU -> X' (written back and re-staged as the next operand
+//      in TMEM) -> K|V = X' @ [Wk|Wv]_relay (N = 256) -> relay attention of each sentence's s row over its
+//      32 tile rows plus the cached h2 keys -> per-sentence attention output (before the relay dense).
+//
+// Arithmetic: prec 1 = bf16x3 split (fp32-class), prec 2 = single bf16 pass; fp32 accumulation, fp32 softmax.
+#include "dsc_common.cuh"
+#include "dsc_tc.cuh"
+
+namespace dsc {
+
+using namespace tc;
+
+// TMEM column map (512 columns allocated)
+constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_A_HI = 256, COL_A_LO = 320;       // satellite kernel
+constexpr uint32_t MIX_ACC_O = 0, MIX_ACC_KV = 128, MIX_A_HI = 384, MIX_A_LO = 448;     // mix kernel
+constexpr int kLoaderWarps = 8, kEpiWarps = 8;
+constexpr int kThreads = (kLoaderWarps + kEpiWarps + 1) * 32;      // 544
+constexpr int kMmaWarp = kLoaderWarps + kEpiWarps;                 // 16
+
+struct Bars {
+  uint64_t w_full;          // weights landed (once)
+  uint64_t a_full;          // operand of the current tile staged in TMEM (256 loader threads)
+  uint64_t a_free;          // every UMMA reading the operand has completed (tcgen05.commit)
+  uint64_t a2_full;         // mix kernel: X' re-staged by the epilogue warps (256 threads)
+  uint64_t acc_full[2];     // accumulator buffer ready (tcgen05.commit)
+  uint64_t acc_free[2];     // accumulator buffer drained by the epilogue warps (256 threads)
+  uint64_t kv_full;         // mix kernel: K|V accumulators ready
+  uint64_t kv_free;         // mix kernel: K|V accumulators drained
+  uint64_t o_full;          // mix kernel: dense (Wo) accumulators ready
+  uint64_t o_free;          // mix kernel: dense accumulators drained
+};
+
+// stage one half row (64 fp32 -> 32 hi + 32 lo packed words) into the thread's TMEM lane
+__device__ __forceinline__ void load_half_row(const float* __restrict__ src, bool valid, uint32_t* hi, uint32_t* lo, bool three) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    float4 v = valid ? __ldg(reinterpret_cast<const float4*>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    split2(v.x, v.y, hi[2 * q], lo[2 * q]);
+    split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
+  }
+  (void)three;
+}
+template <int NPASS>
+__device__ __forceinline__ void store_half_row(uint32_t lane_addr, uint32_t a_hi, uint32_t a_lo, int half,
+                                               const uint32_t* hi, const uint32_t* lo) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    tmem_st8(lane_addr + a_hi + half * 32 + c * 8, hi + c * 8);
+    if (NPASS == 3) tmem_st8(lane_addr + a_lo + half * 32 + c * 8, lo + c * 8);
+  }
+  tmem_st_wait();
+}
+
+// issue the NPASS x 8 UMMAs of one N-group: D[acc_col] = A(tmem) * B(smem rows [n_row0, n_row0 + N))
+template <int NPASS, int N>
+__device__ __forceinline__ void issue_group(uint32_t tmem_base, uint32_t acc_col, uint32_t a_hi, uint32_t a_lo,
+                                            uint32_t b_base, uint32_t b_plane_bytes, uint32_t n_row0) {
+  constexpr uint32_t IDESC = idesc_bf16_f32(128, N);
+#pragma unroll
+  for (int pass = 0; pass < NPASS; ++pass) {
+    const uint32_t a_col = (pass == 1) ? a_lo : a_hi;               // hi*hi, lo*hi, hi*lo
+    const uint32_t pb = (pass == 2) ? 1u : 0u;
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t db = smem_desc_sw128(b_base + (pb * 2 + kb) * b_plane_bytes + n_row0 * 128u + ks * 32u);
+        umma_ts(tmem_base + acc_col, tmem_base + a_col + (uint32_t)(kb * 4 + ks) * 8u, db, IDESC,
+                (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+      }
+  }
+}
+
+// ===================================================================================== satellite phase
+// Packed weight column order (host side, see modules.star_cycles): for head pair g: [q(2 heads x 16) | k | v].
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+star_sat_kernel(const float* __restrict__ X, const float* __restrict__ KVe, const uint8_t* __restrict__ wblob,
+                float* __restrict__ ATT, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sW = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) Bars bars;
+  __shared__ uint32_t tmem_base_s;
+  constexpr uint32_t W_PLANE = 384 * 128;                          // one (part, kb) plane
+  constexpr int parts = (NPASS == 3) ? 2 : 1;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bars.w_full, 1);
+    mbar_init(&bars.a_full, kLoaderWarps * 32);
+    mbar_init(&bars.a_free, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kEpiWarps * 32); }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < kLoaderWarps) {
+    // ------------------------------------------------------------ loaders: X rows -> bf16 hi/lo -> TMEM
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t hi[32], lo[32];
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      load_half_row(X + ((int64_t)t * 128 + row_in_tile) * 128 + half * 64, true, hi, lo, NPASS == 3);
+      mbar_wait(&bars.a_free, (it - 1) & 1);                       // previous tile's UMMAs are done with the operand
+      tc_fence_after();
+      store_half_row<NPASS>(lane_addr, COL_A_HI, COL_A_LO, half, hi, lo);
+      tc_fence_before();
+      mbar_arrive(&bars.a_full);
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      mbar_expect_tx(&bars.w_full, parts * 2 * W_PLANE);
+      for (int p = 0; p < parts * 2; ++p) bulk_g2s(sW + p * W_PLANE, wblob + (size_t)p * W_PLANE, W_PLANE, &bars.w_full);
+      mbar_wait(&bars.w_full, 0);
+      const uint32_t b_base = smem_u32(sW);
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        mbar_wait(&bars.a_full, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          const int b = g & 1, use = it * 2 + (g >> 1);
+          mbar_wait(&bars.acc_free[b], (use - 1) & 1);
+          tc_fence_after();
+          issue_group<NPASS, 96>(tmem_base, b ? COL_ACC1 : COL_ACC0, COL_A_HI, COL_A_LO, b_base, W_PLANE, (uint32_t)g * 96u);
+          umma_commit(&bars.acc_full[b]);
+        }
+        umma_commit(&bars.a_free);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue: satellite attention of one head per warp
+    const int ew = warp - kLoaderWarps;
+    const int quarter = ew & 3, hh = ew >> 2;                      // sentence within the tile, head within the pair
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int up = (lane >= 30) ? 0 : lane + 1;                    // roll(h,-1)[i] = h[(i+1) mod 31]
+    const int dn = (lane == 0) ? 30 : lane - 1;                    // roll(h,+1)[i] = h[(i-1) mod 31]
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int64_t row = (int64_t)t * 128 + quarter * 32 + lane;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        const int b = g & 1, use = it * 2 + (g >> 1);
+        const int head = g * 2 + hh;
+        // e-keys of this row/head (constant over cycles) - issue before waiting on the accumulators
+        float ke[16], ve[16];
+        {
+          const float4* kp = reinterpret_cast<const float4*>(KVe + row * 256 + head * 16);
+          const float4* vp = reinterpret_cast<const float4*>(KVe + row * 256 + 128 + head * 16);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 a = __ldg(kp + q), c = __ldg(vp + q);
+            ke[4*q] = a.x; ke[4*q+1] = a.y; ke[4*q+2] = a.z; ke[4*q+3] = a.w;
+            ve[4*q] = c.x; ve[4*q+1] = c.y; ve[4*q+2] = c.z; ve[4*q+3] = c.w;
+          }
+        }
+        mbar_wait(&bars.acc_full[b], use & 1);
+        tc_fence_after();
+        float q[16], k[16], v[16];
+        const uint32_t col = lane_addr + (b ? COL_ACC1 : COL_ACC0) + hh * 16;
+        tmem_ld16(col, q);
+        tmem_ld16(col + 32, k);
+        tmem_ld16(col + 64, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.acc_free[b]);
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          const float ku = __shfl_sync(0xffffffffu, k[d], up);
+          const float kd = __shfl_sync(0xffffffffu, k[d], dn);
+          const float ks = __shfl_sync(0xffffffffu, k[d], 31);
+          l0 = fmaf(q[d], ku, l0);
+          l1 = fmaf(q[d], k[d], l1);
+          l2 = fmaf(q[d], kd, l2);
+          l3 = fmaf(q[d], ke[d], l3);
+          l4 = fmaf(q[d], ks, l4);
+        }
+        l0 *= 0.25f; l1 *= 0.25f; l2 *= 0.25f; l3 *= 0.25f; l4 *= 0.25f;
+        const float mx = fmaxf(fmaxf(fmaxf(l0, l1), fmaxf(l2, l3)), l4);
+        l0 = expf(l0 - mx); l1 = expf(l1 - mx); l2 = expf(l2 - mx); l3 = expf(l3 - mx); l4 = expf(l4 - mx);
+        const float inv = 1.0f / (l0 + l1 + l2 + l3 + l4);
+        l0 *= inv; l1 *= inv; l2 *= inv; l3 *= inv; l4 *= inv;
+        float o[16];
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          const float vu = __shfl_sync(0xffffffffu, v[d], up);
+          const float vd = __shfl_sync(0xffffffffu, v[d], dn);
+          const float vs = __shfl_sync(0xffffffffu, v[d], 31);
+          float acc = l0 * vu;
+          acc = fmaf(l1, v[d], acc);
+          acc = fmaf(l2, vd, acc);
+          acc = fmaf(l3, ve[d], acc);
+          acc = fmaf(l4, vs, acc);
+          o[d] = (lane == 31) ? 0.f : acc;                         // relay row carries no satellite output
+        }
+        float4* dst = reinterpret_cast<float4*>(ATT + row * 128 + head * 16);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) dst[qd] = make_float4(o[4*qd], o[4*qd+1], o[4*qd+2], o[4*qd+3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+
+// ===================================================================================== mix phase
+// X' = relu(ATT @ Wo_sat + b) (rows 0..30; row 31 keeps s) -> K|V = X' @ [Wk|Wv]_relay -> relay attention.
+// wblob = [Wo_sat planes (4 x 16 KB)] then [Wkv_relay planes (4 x 32 KB)]  (parts = 1: 2 + 2 planes).
+template <int NPASS>
+__global__ void __launch_bounds__(kThreads, 1)
+star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint8_t* __restrict__ wo_blob,
+                const uint8_t* __restrict__ wkv_blob, const float* __restrict__ bias_o, const float* __restrict__ Qr,
+                const float* __restrict__ KV2, int kv2_rows, int n2, float* __restrict__ ATTR, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sWo = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int parts = (NPASS == 3) ? 2 : 1;
+  constexpr uint32_t WO_PLANE = 128 * 128, WKV_PLANE = 256 * 128;
+  uint8_t* sWkv = sWo + parts * 2 * WO_PLANE;
+  __shared__ __align__(8) Bars bars;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(&bars.w_full, 1);
+    mbar_init(&bars.a_full, kLoaderWarps * 32);
+    mbar_init(&bars.a_free, 1);
+    mbar_init(&bars.a2_full, kEpiWarps * 32);
+    mbar_init(&bars.o_full, 1);
+    mbar_init(&bars.o_free, kEpiWarps * 32);
+    mbar_init(&bars.kv_full, 1);
+    mbar_init(&bars.kv_free, kEpiWarps * 32);
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < kLoaderWarps) {
+    const int quarter = warp & 3, half = warp >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int row_in_tile = quarter * 32 + lane;
+    uint32_t hi[32], lo[32];
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      load_half_row(ATT + ((int64_t)t * 128 + row_in_tile) * 128 + half * 64, true, hi, lo, NPASS == 3);
+      mbar_wait(&bars.a_free, (it - 1) & 1);
+      tc_fence_after();
+      store_half_row<NPASS>(lane_addr, MIX_A_HI, MIX_A_LO, half, hi, lo);
+      tc_fence_before();
+      mbar_arrive(&bars.a_full);
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      mbar_expect_tx(&bars.w_full, parts * 2 * (WO_PLANE + WKV_PLANE));
+      for (int p = 0; p < parts * 2; ++p) {
+        bulk_g2s(sWo + p * WO_PLANE, wo_blob + (size_t)p * WO_PLANE, WO_PLANE, &bars.w_full);
+        bulk_g2s(sWkv + p * WKV_PLANE, wkv_blob + (size_t)p * WKV_PLANE, WKV_PLANE, &bars.w_full);
+      }
+      mbar_wait(&bars.w_full, 0);
+      const uint32_t wo_base = smem_u32(sWo), wkv_base = smem_u32(sWkv);
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        mbar_wait(&bars.a_full, it & 1);
+        mbar_wait(&bars.o_free, (it - 1) & 1);
+        tc_fence_after();
+        issue_group<NPASS, 128>(tmem_base, MIX_ACC_O, MIX_A_HI, MIX_A_LO, wo_base, WO_PLANE, 0u);
+        umma_commit(&bars.o_full);
+        mbar_wait(&bars.a2_full, it & 1);
+        mbar_wait(&bars.kv_free, (it - 1) & 1);
+        tc_fence_after();
+        issue_group<NPASS, 256>(tmem_base, MIX_ACC_KV, MIX_A_HI, MIX_A_LO, wkv_base, WKV_PLANE, 0u);
+        umma_commit(&bars.kv_full);
+        umma_commit(&bars.a_free);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int ew = warp - kLoaderWarps;
+    const int quarter = ew & 3, hh = ew >> 2;                      // sentence within the tile, column half
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int64_t row = (int64_t)t * 128 + quarter * 32 + lane;
+      const int64_t sent = (int64_t)t * 4 + quarter;
+      // ---------------- phase 1: X' = relu(acc + b); relay row keeps s; re-stage as the next operand
+      {
+        float* xrow = X + row * 128 + hh * 64;
+        mbar_wait(&bars.o_full, it & 1);
+        tc_fence_after();
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float v[32];
+          tmem_ld32(lane_addr + MIX_ACC_O + hh * 64 + j * 32, v);
+          tmem_ld_wait();
+          if (lane == 31) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              float4 s4 = *reinterpret_cast<const float4*>(xrow + j * 32 + q4 * 4);
+              v[4*q4] = s4.x; v[4*q4+1] = s4.y; v[4*q4+2] = s4.z; v[4*q4+3] = s4.w;
+            }
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_o + hh * 64 + j * 32) + q4);
+              v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
+              v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
+              v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
+              v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
+              *reinterpret_cast<float4*>(xrow + j * 32 + q4 * 4) = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+            }
+          }
+#pragma unroll
+          for (int q2 = 0; q2 < 16; ++q2) split2(v[2*q2], v[2*q2+1], hi[j * 16 + q2], lo[j * 16 + q2]);
+        }
+        tc_fence_before();
+        mbar_arrive(&bars.o_free);
+        store_half_row<NPASS>(lane_addr, MIX_A_HI, MIX_A_LO, hh, hi, lo);
+        tc_fence_before();
+        mbar_arrive(&bars.a2_full);
+      }
+      // ---------------- phase 2: relay attention, 4 heads per warp, lane = key row (and h2 key `lane` if < n2)
+      {
+        const float* qr = Qr + sent * 128 + hh * 64;
+        const float* kv2 = (n2 > 0) ? KV2 + (sent * kv2_rows + lane) * 256 + hh * 64 : nullptr;
+        const bool has2 = lane < n2;
+        mbar_wait(&bars.kv_full, it & 1);
+        tc_fence_after();
+        float w1[4], w2[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float k[16];
+          tmem_ld16(lane_addr + MIX_ACC_KV + hh * 64 + h * 16, k);
+          tmem_ld_wait();
+          float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 qq = __ldg(reinterpret_cast<const float4*>(qr + h * 16) + q4);
+            d1 = fmaf(qq.x, k[4*q4], d1); d1 = fmaf(qq.y, k[4*q4+1], d1);
+            d1 = fmaf(qq.z, k[4*q4+2], d1); d1 = fmaf(qq.w, k[4*q4+3], d1);
+            if (has2) {
+              const float4 kk = __ldg(reinterpret_cast<const float4*>(kv2 + h * 16) + q4);
+              d2 = fmaf(qq.x, kk.x, d2); d2 = fmaf(qq.y, kk.y, d2); d2 = fmaf(qq.z, kk.z, d2); d2 = fmaf(qq.w, kk.w, d2);
+            }
+          }
+          d1 *= 0.25f;
+          d2 = has2 ? d2 * 0.25f : -3.4e38f;
+          const float mx = warp_max(fmaxf(d1, d2));
+          const float e1 = expf(d1 - mx), e2 = has2 ? expf(d2 - mx) : 0.f;
+          const float inv = 1.0f / warp_sum(e1 + e2);
+          w1[h] = e1 * inv;
+          w2[h] = e2 * inv;
+        }
+        float p[64];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float v[16];
+          tmem_ld16(lane_addr + MIX_ACC_KV + 128 + hh * 64 + h * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has2) vv = __ldg(reinterpret_cast<const float4*>(kv2 + 128 + h * 16) + q4);
+            p[h * 16 + 4*q4]     = fmaf(w1[h], v[4*q4],     w2[h] * vv.x);
+            p[h * 16 + 4*q4 + 1] = fmaf(w1[h], v[4*q4 + 1], w2[h] * vv.y);
+            p[h * 16 + 4*q4 + 2] = fmaf(w1[h], v[4*q4 + 2], w2[h] * vv.z);
+            p[h * 16 + 4*q4 + 3] = fmaf(w1[h], v[4*q4 + 3], w2[h] * vv.w);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bars.kv_free);
+        // reduce-scatter the 64 partial sums over the 32 lanes: lane ends with dims 2*lane, 2*lane+1
+#pragma unroll
+        for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < n; ++i) {
+            const float send = upper ? p[i] : p[i + n];
+            const float keep = upper ? p[i + n] : p[i];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        *reinterpret_cast<float2*>(ATTR + sent * 128 + hh * 64 + 2 * lane) = make_float2(p[0], p[1]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace dsc
+
+using namespace dsc;
+
+template <int NPASS>
+static int launch_star_sat(const float* x, const float* kv_e, const void* w, float* att, int n_tiles, cudaStream_t s) {
+  constexpr size_t smem = (size_t)(NPASS == 3 ? 4 : 2) * 384 * 128 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(star_sat_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("dsc_star_sat_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
+  int grid = n_tiles < kSMs ? n_tiles : kSMs;
+  star_sat_kernel<NPASS><<<grid, kThreads, smem, s>>>(x, kv_e, reinterpret_cast<const uint8_t*>(w), att, n_tiles);
+  return check_launch("dsc_star_sat_tc");
+}
+
+extern "C" int dsc_star_sat_tc(const float* x_tile, const float* kv_e, const void* packed_wqkv_grouped, float* att,
+                               int n_sent, int prec, void* stream) {
+  DSC_REQUIRE(x_tile && kv_e && packed_wqkv_grouped && att, "dsc_star_sat_tc: null pointer");
+  DSC_REQUIRE(n_sent >= 0 && (n_sent % 4) == 0, "dsc_star_sat_tc: n_sent must be a multiple of 4 (one tile = 4 sentences)");
+  DSC_REQUIRE(aligned16(x_tile) && aligned16(kv_e) && aligned16(att) && ((uintptr_t)packed_wqkv_grouped & 127u) == 0,
+              "dsc_star_sat_tc: misaligned pointer");
+  DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_sat_tc: prec must be 1 (bf16x3) or 2 (bf16)");
+  if (n_sent == 0) return DSC_OK;
+  return prec == 1 ? launch_star_sat<3>(x_tile, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream))
+                   : launch_star_sat<1>(x_tile, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream));
+}
+
+template <int NPASS>
+static int launch_star_mix(const float* att, float* x, const void* wo, const void* wkv, const float* bias_o,
+                           const float* qr, const float* kv2, int kv2_rows, int n2, float* attr, int n_tiles,
+                           cudaStream_t s) {
+  constexpr size_t smem = (size_t)(NPASS == 3 ? 4 : 2) * (128 + 256) * 128 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(star_mix_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("dsc_star_mix_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
+  int grid = n_tiles < kSMs ? n_tiles : kSMs;
+  star_mix_kernel<NPASS><<<grid, kThreads, smem, s>>>(att, x, reinterpret_cast<const uint8_t*>(wo),
+                                                      reinterpret_cast<const uint8_t*>(wkv), bias_o, qr, kv2, kv2_rows,
+                                                      n2, attr, n_tiles);
+  return check_launch("dsc_star_mix_tc");
+}
+
+extern "C" int dsc_star_mix_tc(const float* att, float* x_tile, const void* packed_wo, const void* packed_wkv_relay,
+                               const float* bias_o, const float* q_relay, const float* kv2, int kv2_rows, int n2,
+                               float* att_relay, int n_sent, int prec, void* stream) {
+  DSC_REQUIRE(att && x_tile && packed_wo && packed_wkv_relay && bias_o && q_relay && att_relay, "dsc_star_mix_tc: null pointer");
+  DSC_REQUIRE(n_sent >= 0 && (n_sent % 4) == 0, "dsc_star_mix_tc: n_sent must be a multiple of 4");
+  DSC_REQUIRE(n2 >= 0 && n2 <= 32 && (n2 == 0 || (kv2 && n2 <= kv2_rows)), "dsc_star_mix_tc: bad h2 key count");
+  DSC_REQUIRE(aligned16(att) && aligned16(x_tile) && aligned16(q_relay) && aligned16(att_relay) && aligned16(bias_o) &&
+              (!kv2 || aligned16(kv2)), "dsc_star_mix_tc: misaligned pointer");
+  DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_mix_tc: prec must be 1 (bf16x3) or 2 (bf16)");
+  if (n_sent == 0) return DSC_OK;
+  return prec == 1 ? launch_star_mix<3>(att, x_tile, packed_wo, packed_wkv_relay, bias_o, q_relay, kv2, kv2_rows, n2,
+                                        att_relay, n_sent / 4, as_stream(stream))
+                   : launch_star_mix<1>(att, x_tile, packed_wo, packed_wkv_relay, bias_o, q_relay, kv2, kv2_rows, n2,
+                                        att_relay, n_sent / 4, as_stream(stream));
+}

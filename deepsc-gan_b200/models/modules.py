@@ -132,11 +132,17 @@ class sublayer1(nn.Module):
 
     def _packed(self, which: str) -> torch.Tensor:
         """Concatenated projection weights: 'qkv' [128,384], 'kv' [128,256]."""
-        ws = {"qkv": (self.wq, self.wk, self.wv), "kv": (self.wk, self.wv)}[which]
+        ws = {"qkv": (self.wq, self.wk, self.wv), "kv": (self.wk, self.wv),
+              "qkv_grouped": (self.wq, self.wk, self.wv)}[which]
         key = tuple((w.kernel._version, w.kernel.data_ptr()) for w in ws)
         hit = self._cache.get(which)
         if hit is None or hit[0] != key:
-            hit = (key, torch.cat([w.kernel.detach() for w in ws], dim=1).contiguous())
+            if which == "qkv_grouped":      # head pairs g: [wq[:,32g:32g+32] | wk[...] | wv[...]] (dsc_star_sat_tc)
+                cols = [w.kernel.detach()[:, 32 * g:32 * g + 32] for g in range(4) for w in ws]
+                packed = torch.cat(cols, dim=1).contiguous()
+            else:
+                packed = torch.cat([w.kernel.detach() for w in ws], dim=1).contiguous()
+            hit = (key, packed)
             self._cache[which] = hit
         return hit[1]
 
@@ -192,6 +198,7 @@ class StarWorkspace:
         self.kv_e = torch.empty((n_sent * 32, 256), **f)
         self.att = torch.empty((n_sent * 32, 128), **f)
         self.att_r = torch.empty((n_sent, 128), **f)
+        self.q_r = torch.empty((n_sent, 128), **f)
 
 
 def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_num: int,
@@ -210,8 +217,21 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
     if not kv_e_ready:
         _lib.linear(e2, sat._packed("kv"), None, out=ws.kv_e, prec=PREC)
     ws.x.copy_(e_tile)
-    w_qkv_s, w_qkv_r = sat._packed("qkv"), relay._packed("qkv")
     s_rows = ws.x[:, 31, :]
+    if PREC != 0 and S % 4 == 0:
+        # tcgen05 path: two fused persistent kernels per cycle (projection + satellite attention; dense + relay
+        # k|v projection + relay attention) and two per-sentence Dense calls for the relay node.
+        w_g, wo, bo = sat._packed("qkv_grouped"), sat.dense.kernel.detach(), sat.dense.bias.detach()
+        wkv_r, wq_r = relay._packed("kv"), relay.wq.kernel.detach()
+        _lib.linear(s_rows, wq_r, None, out=ws.q_r, prec=PREC)
+        for c in range(cycle_num):
+            _lib.star_sat_tc(ws.x, ws.kv_e, w_g, ws.att, S, PREC)
+            _lib.star_mix_tc(ws.att, ws.x, wo, bo, wkv_r, ws.q_r, kv2, n2, ws.att_r, S, PREC)
+            _lib.linear(ws.att_r, relay.dense.kernel.detach(), relay.dense.bias.detach(), act=1, out=s_rows, prec=PREC)
+            if c + 1 < cycle_num:
+                _lib.linear(s_rows, wq_r, None, out=ws.q_r, prec=PREC)
+        return ws.x
+    w_qkv_s, w_qkv_r = sat._packed("qkv"), relay._packed("qkv")
     for _ in range(cycle_num):
         _lib.linear(x2, w_qkv_s, None, out=ws.qkv, prec=PREC)
         _lib.star_satellite_attn(ws.qkv, ws.kv_e, ws.att, S)

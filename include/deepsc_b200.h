@@ -92,6 +92,22 @@ int dsc_star_pack(const float* src, float* tile, int n_sent, void* stream);
  * {h[i+1], h[i], h[i-1], e[i], s} (cyclic neighbours, no mask); row 31 is zero-filled. */
 int dsc_star_satellite_attn(const float* qkv, const float* kv_e, float* att, int n_sent, void* stream);
 
+/* K2+K3 fused on tcgen05: att = satellite_attention(x_tile @ [wq|wk|wv]_satellite, kv_e) without materialising
+ * the [rows,384] projection.  packed_wqkv_grouped = dsc_pack_weight of the [128,384] matrix whose columns are
+ * ordered by head pair g = 0..3: [wq[:,32g:32g+32] | wk[:,32g:32g+32] | wv[:,32g:32g+32]].  n_sent % 4 == 0
+ * (one persistent-CTA tile = 4 sentences = 128 TMEM lanes).  prec 1 = bf16x3, 2 = bf16. */
+int dsc_star_sat_tc(const float* x_tile, const float* kv_e, const void* packed_wqkv_grouped, float* att,
+                    int n_sent, int prec, void* stream);
+
+/* K2+K4 fused on tcgen05: x_tile rows 0..30 <- relu(att @ wo_sat + bias_o) (row 31 keeps s), then
+ * k|v = x_tile @ [wk|wv]_relay in TMEM and the relay attention of each sentence's query q_relay [n_sent,128]
+ * (= s @ wq_relay) over its 32 tile rows plus the first n2 rows of kv2 [n_sent, kv2_rows, 256];
+ * att_relay [n_sent,128] is the attention output before the relay dense layer.  packed_wo = dsc_pack_weight of
+ * wo_sat [128,128], packed_wkv_relay of [wk|wv]_relay [128,256]. */
+int dsc_star_mix_tc(const float* att, float* x_tile, const void* packed_wo, const void* packed_wkv_relay,
+                    const float* bias_o, const float* q_relay, const float* kv2, int kv2_rows, int n2,
+                    float* att_relay, int n_sent, int prec, void* stream);
+
 /* K4: relay attention of one star cycle (models/modules.py:303-306, 375-378).
  * qkv_r [n_sent*32, 384] = updated tile @ [wq|wk|wv] of the relay weights; the query is row 31,
  * keys/values are row 31 (s), rows 0..30 (h) and, for the decoder, the first n2 rows of

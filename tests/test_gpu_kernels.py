@@ -103,13 +103,17 @@ def test_star_pack_mean_row(L, dev):
     assert torch.allclose(t[:, 31], e.mean(1), atol=1e-6)
 
 
+@pytest.mark.parametrize("prec,tol", [(0, 5e-6), (1, 1e-4), (2, 5e-2)])
 @pytest.mark.parametrize("n2", [0, 1, 17, 30])
-def test_star_cycle_kernels_match_literal_oracle(L, dev, n2):
-    """One full cycle (satellite + relay) against the literal 5-key concat form of modules.py:289-306."""
+def test_star_cycle_kernels_match_literal_oracle(L, dev, n2, prec, tol, monkeypatch):
+    """Full cycles (satellite + relay) against the literal 5-key concat form of modules.py:289-306, for the
+    fp32 kernels (prec 0) and the fused tcgen05 kernels (prec 1 bf16x3, prec 2 bf16)."""
+    import deepsc_gan_b200.models.modules as M0
+    monkeypatch.setattr(M0, "PREC", prec)
     P = _cases.params("Transeiver_Star", gain=3.0)
     pre = "semantic_decoder/dec_layers"
     g = torch.Generator().manual_seed(10 + n2)
-    S = 6
+    S = 8
     e = torch.randn(S, 31, 128, generator=g)
     h2 = torch.randn(S, 30, 128, generator=g)[:, :n2] if n2 else None
     h_ref, s_ref = O._star_cycles(P, pre, e, h2, 1, "multi_att_relay")
@@ -129,9 +133,11 @@ def test_star_cycle_kernels_match_literal_oracle(L, dev, n2):
         kv2 = torch.zeros(S, 30, 256, device=dev)
         kv2[:, :n2] = L.linear(h2.reshape(-1, 128).to(dev), relay._packed("kv"), None).view(S, n2, 256)
     x = M.star_cycles(tile, sat, relay, 1, kv2, n2).clone()
-    assert rel_err(x[:, :31], h_ref) < 5e-6 and rel_err(x[:, 31], s_ref) < 5e-6
+    torch.cuda.synchronize()
+    assert rel_err(x[:, :31], h_ref) < tol and rel_err(x[:, 31], s_ref) < tol
     x3 = M.star_cycles(tile, sat, relay, 3, kv2, n2)
-    assert rel_err(x3[:, :31], h_ref3) < 2e-5 and rel_err(x3[:, 31], s_ref3) < 2e-5
+    torch.cuda.synchronize()
+    assert rel_err(x3[:, :31], h_ref3) < 4 * tol and rel_err(x3[:, 31], s_ref3) < 4 * tol
 
 
 @pytest.mark.parametrize("lq,lk,mode", [(31, 31, "pad"), (30, 30, "combined"), (1, 17, "ids"), (30, 31, "pad"), (7, 7, "none")])
@@ -330,3 +336,24 @@ def test_linear_tensor_core_row_skip_strided(L, dev):
     tile = torch.zeros((4, 32, 128), device=dev)
     L.linear(x[:4], w, None, out=tile[:, 31, :], prec=1)
     assert rel_err(tile[:, 31, :], ref[:4]) < 3e-5 and float(tile[:, :31].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec,tol", [(1, 1e-4), (2, 5e-2)])
+@pytest.mark.parametrize("S", [4, 600, 2368])
+def test_star_sat_fused_matches_unfused(L, dev, S, prec, tol):
+    """dsc_star_sat_tc (UMMA projection + shuffle attention) == dsc_linear(fp32) + dsc_star_satellite_attn."""
+    import deepsc_gan_b200.models.modules as M
+    g = torch.Generator().manual_seed(S)
+    sat = M.sublayer1(128, 8).to(dev)
+    with torch.no_grad():
+        for w in (sat.wq, sat.wk):
+            w.kernel.mul_(3.0)
+    x = torch.randn(S, 32, 128, generator=g).to(dev)
+    kv_e = torch.randn(S * 32, 256, generator=g).to(dev)
+    qkv = L.linear(x.view(S * 32, 128), sat._packed("qkv"), None)
+    ref = torch.empty(S * 32, 128, device=dev)
+    L.star_satellite_attn(qkv, kv_e, ref, S)
+    got = torch.full((S * 32, 128), 5.0, device=dev)
+    L.star_sat_tc(x, kv_e, sat._packed("qkv_grouped"), got, S, prec)
+    torch.cuda.synchronize()
+    assert rel_err(got, ref) < tol
