@@ -31,8 +31,10 @@ _SIGNATURES = {
     "dsc_add_layernorm": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "dsc_star_pack": (C.c_int, [vp, vp, i32, vp]),
     "dsc_star_satellite_attn": (C.c_int, [vp, vp, vp, i32, vp]),
-    "dsc_star_sat_tc": (C.c_int, [vp, vp, vp, vp, i32, i32, vp]),
-    "dsc_star_mix_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp]),
+    "dsc_star_sat_tc": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, vp]),
+    "dsc_star_interleave": (C.c_int, [vp, i64, vp, i32, i32, i32, vp]),
+    "dsc_star_kv2_put": (C.c_int, [vp, vp, i32, i32, vp]),
+    "dsc_star_mix_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "dsc_star_relay_attn": (C.c_int, [vp, vp, i32, i32, vp, i32, vp]),
     "dsc_mha_attention": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,
                                     i32, i32, i32, vp]),
@@ -208,30 +210,48 @@ def star_satellite_attn(qkv: torch.Tensor, kv_e: torch.Tensor, att: torch.Tensor
     return att
 
 
-def star_sat_tc(x_tile: torch.Tensor, kv_e: torch.Tensor, w_grouped: torch.Tensor, att: torch.Tensor, n_sent: int,
-                prec: int) -> torch.Tensor:
-    """Fused projection + satellite attention; w_grouped is the [128,384] head-pair-grouped fp32 weight."""
-    _need_cuda(x_tile, kv_e, w_grouped, att)
-    assert x_tile.is_contiguous() and kv_e.is_contiguous() and att.is_contiguous()
+def star_interleave(src: torch.Tensor, dst: torch.Tensor, group_rows: int) -> torch.Tensor:
+    """Row-major [n_groups, group_rows, width] (contiguous within a group) -> interleaved [group][width/4][rows][4]."""
+    _need_cuda(src, dst)
+    assert src.dim() == 3 and src.shape[1] == group_rows and src.stride(2) == 1 and src.stride(1) == src.shape[2]
+    assert dst.is_contiguous() and dst.numel() == src.numel()
+    _check(load().dsc_star_interleave(_f32(src).data_ptr(), src.stride(0), dst.data_ptr(), src.shape[0], group_rows,
+                                      src.shape[2], _stream()), "dsc_star_interleave")
+    return dst
+
+
+def star_kv2_put(vals: torch.Tensor, kv2i: torch.Tensor, row_index: int) -> None:
+    """vals [n_sent, 256] -> row `row_index` of the interleaved h2 cache [n_sent, 64, 32, 4]."""
+    _need_cuda(vals, kv2i)
+    assert vals.is_contiguous() and vals.shape[1] == 256 and kv2i.is_contiguous()
+    _check(load().dsc_star_kv2_put(vals.data_ptr(), kv2i.data_ptr(), row_index, vals.shape[0], _stream()),
+           "dsc_star_kv2_put")
+
+
+def star_sat_tc(xi: torch.Tensor, s_relay: torch.Tensor, kvei: torch.Tensor, w_grouped: torch.Tensor, atti: torch.Tensor,
+                n_sent: int, prec: int) -> torch.Tensor:
+    """Fused projection + satellite attention on interleaved tiles; w_grouped = head-pair-grouped [128,384] weight."""
+    _need_cuda(xi, s_relay, kvei, w_grouped, atti)
+    assert xi.is_contiguous() and kvei.is_contiguous() and atti.is_contiguous() and s_relay.is_contiguous()
     blob = packed_weight(w_grouped, 384)
-    _check(load().dsc_star_sat_tc(x_tile.data_ptr(), kv_e.data_ptr(), blob.data_ptr(), att.data_ptr(), n_sent, prec,
-                                  _stream()), "dsc_star_sat_tc")
-    return att
+    _check(load().dsc_star_sat_tc(xi.data_ptr(), s_relay.data_ptr(), kvei.data_ptr(), blob.data_ptr(), atti.data_ptr(),
+                                  n_sent, prec, _stream()), "dsc_star_sat_tc")
+    return atti
 
 
-def star_mix_tc(att: torch.Tensor, x_tile: torch.Tensor, wo: torch.Tensor, bias_o: torch.Tensor, wkv_relay: torch.Tensor,
-                q_relay: torch.Tensor, kv2: Optional[torch.Tensor], n2: int, att_relay: torch.Tensor, n_sent: int,
-                prec: int) -> torch.Tensor:
-    """Fused Wo dense + relu (in place on x_tile rows 0..30) + relay k|v projection + relay attention."""
-    _need_cuda(att, x_tile, wo, bias_o, wkv_relay, q_relay, kv2, att_relay)
-    assert att.is_contiguous() and x_tile.is_contiguous() and q_relay.is_contiguous() and att_relay.is_contiguous()
-    kv2_rows = 0 if kv2 is None else kv2.shape[1]
-    if kv2 is not None:
-        assert kv2.is_contiguous() and kv2.shape[2] == 256
-    _check(load().dsc_star_mix_tc(att.data_ptr(), x_tile.data_ptr(), packed_weight(wo, 128).data_ptr(),
-                                  packed_weight(wkv_relay, 256).data_ptr(), bias_o.data_ptr(), q_relay.data_ptr(),
-                                  _ptr(kv2), kv2_rows, n2, att_relay.data_ptr(), n_sent, prec, _stream()),
-           "dsc_star_mix_tc")
+def star_mix_tc(atti: torch.Tensor, xi: torch.Tensor, x_rowmajor: Optional[torch.Tensor], s_relay: torch.Tensor,
+                wo: torch.Tensor, bias_o: torch.Tensor, wkv_relay: torch.Tensor, q_relay: torch.Tensor,
+                kv2i: Optional[torch.Tensor], n2: int, att_relay: torch.Tensor, n_sent: int, prec: int) -> torch.Tensor:
+    """Fused Wo dense + relu + relay k|v projection + relay attention (see include/deepsc_b200.h)."""
+    _need_cuda(atti, xi, x_rowmajor, s_relay, wo, bias_o, wkv_relay, q_relay, kv2i, att_relay)
+    for t in (atti, xi, s_relay, q_relay, att_relay):
+        assert t.is_contiguous()
+    assert x_rowmajor is None or x_rowmajor.is_contiguous()
+    assert kv2i is None or (kv2i.is_contiguous() and kv2i.numel() == n_sent * 8192)
+    _check(load().dsc_star_mix_tc(atti.data_ptr(), xi.data_ptr(), _ptr(x_rowmajor), s_relay.data_ptr(),
+                                  packed_weight(wo, 128).data_ptr(), packed_weight(wkv_relay, 256).data_ptr(),
+                                  bias_o.data_ptr(), q_relay.data_ptr(), _ptr(kv2i), n2, att_relay.data_ptr(), n_sent,
+                                  prec, _stream()), "dsc_star_mix_tc")
     return att_relay
 
 

@@ -10,6 +10,12 @@
 //      in TMEM) -> K|V = X' @ [Wk|Wv]_relay (N = 256) -> relay attention of each sentence's s row over its
 //      32 tile rows plus the cached h2 keys -> per-sentence attention output (before the relay dense).
 //
+// Data layout in HBM ("interleaved tile"): thread t of the CTA owns row t (TMEM lane t), so every tensor the
+// warps stream per row is stored [tile][k/4][row][4 floats]: for a fixed k/4 the 32 lanes of a warp read or
+// write 512 contiguous bytes (4 L1 wavefronts instead of 32 for a row-major [row][k] layout).
+//   XI / ATTI [n_tiles][32][128][4], KVEI [n_tiles][64][128][4], KV2I [n_sent][64][32][4].
+// The relay node lives in its own compact buffer S [n_sent][128] (row 31 of a tile is not stored in XI).
+//
 // Arithmetic: prec 1 = bf16x3 split (fp32-class), prec 2 = single bf16 pass; fp32 accumulation, fp32 softmax.
 #include "dsc_common.cuh"
 #include "dsc_tc.cuh"
@@ -39,14 +45,15 @@ struct Bars {
 };
 
 // stage one half row (64 fp32 -> 32 hi + 32 lo packed words) into the thread's TMEM lane
-__device__ __forceinline__ void load_half_row(const float* __restrict__ src, bool valid, uint32_t* hi, uint32_t* lo, bool three) {
+// src points at element (k4 = 0, this row); consecutive k4 are `stride4` float4 apart (128 for the interleaved
+// tile layout, 1 for a compact row such as the relay buffer).
+__device__ __forceinline__ void load_half_row(const float4* __restrict__ src, int stride4, uint32_t* hi, uint32_t* lo) {
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    float4 v = valid ? __ldg(reinterpret_cast<const float4*>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = __ldg(src + (int64_t)q * stride4);
     split2(v.x, v.y, hi[2 * q], lo[2 * q]);
     split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
   }
-  (void)three;
 }
 template <int NPASS>
 __device__ __forceinline__ void store_half_row(uint32_t lane_addr, uint32_t a_hi, uint32_t a_lo, int half,
@@ -83,8 +90,8 @@ __device__ __forceinline__ void issue_group(uint32_t tmem_base, uint32_t acc_col
 // Packed weight column order (host side, see modules.star_cycles): for head pair g: [q(2 heads x 16) | k | v].
 template <int NPASS>
 __global__ void __launch_bounds__(kThreads, 1)
-star_sat_kernel(const float* __restrict__ X, const float* __restrict__ KVe, const uint8_t* __restrict__ wblob,
-                float* __restrict__ ATT, int n_tiles) {
+star_sat_kernel(const float* __restrict__ XI, const float* __restrict__ Sbuf, const float* __restrict__ KVEI,
+                const uint8_t* __restrict__ wblob, float* __restrict__ ATTI, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sW = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) Bars bars;
@@ -114,7 +121,10 @@ star_sat_kernel(const float* __restrict__ X, const float* __restrict__ KVe, cons
     uint32_t hi[32], lo[32];
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      load_half_row(X + ((int64_t)t * 128 + row_in_tile) * 128 + half * 64, true, hi, lo, NPASS == 3);
+      if (lane == 31)   // relay row: compact buffer S[sentence][128]
+        load_half_row(reinterpret_cast<const float4*>(Sbuf + ((int64_t)t * 4 + quarter) * 128 + half * 64), 1, hi, lo);
+      else
+        load_half_row(reinterpret_cast<const float4*>(XI + (int64_t)t * 16384) + (half * 16) * 128 + row_in_tile, 128, hi, lo);
       mbar_wait(&bars.a_free, (it - 1) & 1);                       // previous tile's UMMAs are done with the operand
       tc_fence_after();
       store_half_row<NPASS>(lane_addr, COL_A_HI, COL_A_LO, half, hi, lo);
@@ -153,7 +163,9 @@ star_sat_kernel(const float* __restrict__ X, const float* __restrict__ KVe, cons
     const int dn = (lane == 0) ? 30 : lane - 1;                    // roll(h,+1)[i] = h[(i-1) mod 31]
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int64_t row = (int64_t)t * 128 + quarter * 32 + lane;
+      const int row_in_tile = quarter * 32 + lane;
+      const float4* kve = reinterpret_cast<const float4*>(KVEI + (int64_t)t * 32768) + row_in_tile;
+      float4* att = reinterpret_cast<float4*>(ATTI + (int64_t)t * 16384) + row_in_tile;
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         const int b = g & 1, use = it * 2 + (g >> 1);
@@ -161,11 +173,11 @@ star_sat_kernel(const float* __restrict__ X, const float* __restrict__ KVe, cons
         // e-keys of this row/head (constant over cycles) - issue before waiting on the accumulators
         float ke[16], ve[16];
         {
-          const float4* kp = reinterpret_cast<const float4*>(KVe + row * 256 + head * 16);
-          const float4* vp = reinterpret_cast<const float4*>(KVe + row * 256 + 128 + head * 16);
+          const float4* kp = kve + (head * 4) * 128;
+          const float4* vp = kve + (32 + head * 4) * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float4 a = __ldg(kp + q), c = __ldg(vp + q);
+            float4 a = __ldg(kp + q * 128), c = __ldg(vp + q * 128);
             ke[4*q] = a.x; ke[4*q+1] = a.y; ke[4*q+2] = a.z; ke[4*q+3] = a.w;
             ve[4*q] = c.x; ve[4*q+1] = c.y; ve[4*q+2] = c.z; ve[4*q+3] = c.w;
           }
@@ -210,9 +222,8 @@ star_sat_kernel(const float* __restrict__ X, const float* __restrict__ KVe, cons
           acc = fmaf(l4, vs, acc);
           o[d] = (lane == 31) ? 0.f : acc;                         // relay row carries no satellite output
         }
-        float4* dst = reinterpret_cast<float4*>(ATT + row * 128 + head * 16);
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) dst[qd] = make_float4(o[4*qd], o[4*qd+1], o[4*qd+2], o[4*qd+3]);
+        for (int qd = 0; qd < 4; ++qd) att[(head * 4 + qd) * 128] = make_float4(o[4*qd], o[4*qd+1], o[4*qd+2], o[4*qd+3]);
       }
     }
   }
@@ -227,9 +238,10 @@ star_sat_kernel(const float* __restrict__ X, const float* __restrict__ KVe, cons
 // wblob = [Wo_sat planes (4 x 16 KB)] then [Wkv_relay planes (4 x 32 KB)]  (parts = 1: 2 + 2 planes).
 template <int NPASS>
 __global__ void __launch_bounds__(kThreads, 1)
-star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint8_t* __restrict__ wo_blob,
+star_mix_kernel(const float* __restrict__ ATTI, float* __restrict__ XI, float* __restrict__ Xrow,
+                const float* __restrict__ Sbuf, const uint8_t* __restrict__ wo_blob,
                 const uint8_t* __restrict__ wkv_blob, const float* __restrict__ bias_o, const float* __restrict__ Qr,
-                const float* __restrict__ KV2, int kv2_rows, int n2, float* __restrict__ ATTR, int n_tiles) {
+                const float* __restrict__ KV2I, int n2, float* __restrict__ ATTR, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sWo = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int parts = (NPASS == 3) ? 2 : 1;
@@ -263,7 +275,7 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
     uint32_t hi[32], lo[32];
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      load_half_row(ATT + ((int64_t)t * 128 + row_in_tile) * 128 + half * 64, true, hi, lo, NPASS == 3);
+      load_half_row(reinterpret_cast<const float4*>(ATTI + (int64_t)t * 16384) + (half * 16) * 128 + row_in_tile, 128, hi, lo);
       mbar_wait(&bars.a_free, (it - 1) & 1);
       tc_fence_after();
       store_half_row<NPASS>(lane_addr, MIX_A_HI, MIX_A_LO, half, hi, lo);
@@ -301,11 +313,13 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int64_t row = (int64_t)t * 128 + quarter * 32 + lane;
+      const int row_in_tile = quarter * 32 + lane;
       const int64_t sent = (int64_t)t * 4 + quarter;
       // ---------------- phase 1: X' = relu(acc + b); relay row keeps s; re-stage as the next operand
       {
-        float* xrow = X + row * 128 + hh * 64;
+        float4* xi = reinterpret_cast<float4*>(XI + (int64_t)t * 16384) + (hh * 16) * 128 + row_in_tile;
+        float4* xr = Xrow ? reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + hh * 64) : nullptr;
+        const float4* srow = reinterpret_cast<const float4*>(Sbuf + sent * 128 + hh * 64);
         mbar_wait(&bars.o_full, it & 1);
         tc_fence_after();
         uint32_t hi[32], lo[32];
@@ -317,8 +331,9 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
           if (lane == 31) {
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
-              float4 s4 = *reinterpret_cast<const float4*>(xrow + j * 32 + q4 * 4);
+              float4 s4 = __ldg(srow + j * 8 + q4);
               v[4*q4] = s4.x; v[4*q4+1] = s4.y; v[4*q4+2] = s4.z; v[4*q4+3] = s4.w;
+              if (xr) xr[j * 8 + q4] = s4;
             }
           } else {
 #pragma unroll
@@ -328,7 +343,8 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
               v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
               v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
               v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
-              *reinterpret_cast<float4*>(xrow + j * 32 + q4 * 4) = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+              const float4 o4 = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+              if (xr) xr[j * 8 + q4] = o4; else xi[(j * 8 + q4) * 128] = o4;
             }
           }
 #pragma unroll
@@ -343,7 +359,8 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
       // ---------------- phase 2: relay attention, 4 heads per warp, lane = key row (and h2 key `lane` if < n2)
       {
         const float* qr = Qr + sent * 128 + hh * 64;
-        const float* kv2 = (n2 > 0) ? KV2 + (sent * kv2_rows + lane) * 256 + hh * 64 : nullptr;
+        // KV2I [sentence][64 k4][32 rows][4]: k columns are k4 0..31, v columns k4 32..63; lane = h2 row
+        const float4* kv2 = reinterpret_cast<const float4*>(KV2I + sent * 8192) + (hh * 16) * 32 + lane;
         const bool has2 = lane < n2;
         mbar_wait(&bars.kv_full, it & 1);
         tc_fence_after();
@@ -360,7 +377,7 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
             d1 = fmaf(qq.x, k[4*q4], d1); d1 = fmaf(qq.y, k[4*q4+1], d1);
             d1 = fmaf(qq.z, k[4*q4+2], d1); d1 = fmaf(qq.w, k[4*q4+3], d1);
             if (has2) {
-              const float4 kk = __ldg(reinterpret_cast<const float4*>(kv2 + h * 16) + q4);
+              const float4 kk = __ldg(kv2 + (h * 4 + q4) * 32);
               d2 = fmaf(qq.x, kk.x, d2); d2 = fmaf(qq.y, kk.y, d2); d2 = fmaf(qq.z, kk.z, d2); d2 = fmaf(qq.w, kk.w, d2);
             }
           }
@@ -381,7 +398,7 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has2) vv = __ldg(reinterpret_cast<const float4*>(kv2 + 128 + h * 16) + q4);
+            if (has2) vv = __ldg(kv2 + (32 + h * 4 + q4) * 32);
             p[h * 16 + 4*q4]     = fmaf(w1[h], v[4*q4],     w2[h] * vv.x);
             p[h * 16 + 4*q4 + 1] = fmaf(w1[h], v[4*q4 + 1], w2[h] * vv.y);
             p[h * 16 + 4*q4 + 2] = fmaf(w1[h], v[4*q4 + 2], w2[h] * vv.z);
@@ -410,58 +427,111 @@ star_mix_kernel(const float* __restrict__ ATT, float* __restrict__ X, const uint
   if (warp == kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
 
+
+// ===================================================================================== layout helpers
+// row-major [n_groups*R rows][width] -> interleaved [group][width/4][R][4].  One CTA per (group, 32-column slab).
+template <int R>
+__global__ void __launch_bounds__(256)
+interleave_kernel(const float* __restrict__ src, int64_t src_group_stride, float* __restrict__ dst, int width) {
+  __shared__ float4 tile[R][9];
+  const int g = blockIdx.x, slab = blockIdx.y;
+  const float* in = src + (int64_t)g * src_group_stride + slab * 32;
+  for (int idx = threadIdx.x; idx < R * 8; idx += 256) {
+    const int row = idx >> 3, c4 = idx & 7;
+    tile[row][c4] = __ldg(reinterpret_cast<const float4*>(in + (int64_t)row * width) + c4);
+  }
+  __syncthreads();
+  float4* out = reinterpret_cast<float4*>(dst + (int64_t)g * R * width) + (int64_t)slab * 8 * R;
+  for (int idx = threadIdx.x; idx < R * 8; idx += 256) {
+    const int k4 = idx / R, row = idx % R;
+    out[k4 * R + row] = tile[row][k4];
+  }
+}
+
+// scatter one h2 row per sentence into KV2I: vals [n_sent][256] -> kv2i[sent][k4][row_index][4]
+__global__ void __launch_bounds__(256)
+kv2_put_kernel(const float* __restrict__ vals, float* __restrict__ kv2i, int row_index, int n_sent) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_sent * 64) return;
+  const int sent = idx >> 6, k4 = idx & 63;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(vals) + idx);
+  reinterpret_cast<float4*>(kv2i)[((int64_t)sent * 64 + k4) * 32 + row_index] = v;
+}
+
 }  // namespace dsc
 
 using namespace dsc;
 
 template <int NPASS>
-static int launch_star_sat(const float* x, const float* kv_e, const void* w, float* att, int n_tiles, cudaStream_t s) {
+static int launch_star_sat(const float* x, const float* sbuf, const float* kv_e, const void* w, float* att, int n_tiles, cudaStream_t s) {
   constexpr size_t smem = (size_t)(NPASS == 3 ? 4 : 2) * 384 * 128 + 1024;
   cudaError_t e = cudaFuncSetAttribute(star_sat_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("dsc_star_sat_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
   int grid = n_tiles < kSMs ? n_tiles : kSMs;
-  star_sat_kernel<NPASS><<<grid, kThreads, smem, s>>>(x, kv_e, reinterpret_cast<const uint8_t*>(w), att, n_tiles);
+  star_sat_kernel<NPASS><<<grid, kThreads, smem, s>>>(x, sbuf, kv_e, reinterpret_cast<const uint8_t*>(w), att, n_tiles);
   return check_launch("dsc_star_sat_tc");
 }
 
-extern "C" int dsc_star_sat_tc(const float* x_tile, const float* kv_e, const void* packed_wqkv_grouped, float* att,
-                               int n_sent, int prec, void* stream) {
-  DSC_REQUIRE(x_tile && kv_e && packed_wqkv_grouped && att, "dsc_star_sat_tc: null pointer");
+extern "C" int dsc_star_sat_tc(const float* x_tile, const float* s_relay, const float* kv_e, const void* packed_wqkv_grouped,
+                               float* att, int n_sent, int prec, void* stream) {
+  DSC_REQUIRE(x_tile && s_relay && kv_e && packed_wqkv_grouped && att, "dsc_star_sat_tc: null pointer");
   DSC_REQUIRE(n_sent >= 0 && (n_sent % 4) == 0, "dsc_star_sat_tc: n_sent must be a multiple of 4 (one tile = 4 sentences)");
   DSC_REQUIRE(aligned16(x_tile) && aligned16(kv_e) && aligned16(att) && ((uintptr_t)packed_wqkv_grouped & 127u) == 0,
               "dsc_star_sat_tc: misaligned pointer");
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_sat_tc: prec must be 1 (bf16x3) or 2 (bf16)");
   if (n_sent == 0) return DSC_OK;
-  return prec == 1 ? launch_star_sat<3>(x_tile, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream))
-                   : launch_star_sat<1>(x_tile, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream));
+  return prec == 1 ? launch_star_sat<3>(x_tile, s_relay, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream))
+                   : launch_star_sat<1>(x_tile, s_relay, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream));
 }
 
 template <int NPASS>
-static int launch_star_mix(const float* att, float* x, const void* wo, const void* wkv, const float* bias_o,
-                           const float* qr, const float* kv2, int kv2_rows, int n2, float* attr, int n_tiles,
+static int launch_star_mix(const float* att, float* x, float* xrow, const float* sbuf, const void* wo, const void* wkv,
+                           const float* bias_o, const float* qr, const float* kv2, int n2, float* attr, int n_tiles,
                            cudaStream_t s) {
   constexpr size_t smem = (size_t)(NPASS == 3 ? 4 : 2) * (128 + 256) * 128 + 1024;
   cudaError_t e = cudaFuncSetAttribute(star_mix_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("dsc_star_mix_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
   int grid = n_tiles < kSMs ? n_tiles : kSMs;
-  star_mix_kernel<NPASS><<<grid, kThreads, smem, s>>>(att, x, reinterpret_cast<const uint8_t*>(wo),
-                                                      reinterpret_cast<const uint8_t*>(wkv), bias_o, qr, kv2, kv2_rows,
-                                                      n2, attr, n_tiles);
+  star_mix_kernel<NPASS><<<grid, kThreads, smem, s>>>(att, x, xrow, sbuf, reinterpret_cast<const uint8_t*>(wo),
+                                                      reinterpret_cast<const uint8_t*>(wkv), bias_o, qr, kv2, n2, attr,
+                                                      n_tiles);
   return check_launch("dsc_star_mix_tc");
 }
 
-extern "C" int dsc_star_mix_tc(const float* att, float* x_tile, const void* packed_wo, const void* packed_wkv_relay,
-                               const float* bias_o, const float* q_relay, const float* kv2, int kv2_rows, int n2,
+extern "C" int dsc_star_mix_tc(const float* att, float* x_tile, float* x_rowmajor, const float* s_relay,
+                               const void* packed_wo, const void* packed_wkv_relay,
+                               const float* bias_o, const float* q_relay, const float* kv2, int n2,
                                float* att_relay, int n_sent, int prec, void* stream) {
-  DSC_REQUIRE(att && x_tile && packed_wo && packed_wkv_relay && bias_o && q_relay && att_relay, "dsc_star_mix_tc: null pointer");
+  DSC_REQUIRE(att && x_tile && s_relay && packed_wo && packed_wkv_relay && bias_o && q_relay && att_relay, "dsc_star_mix_tc: null pointer");
   DSC_REQUIRE(n_sent >= 0 && (n_sent % 4) == 0, "dsc_star_mix_tc: n_sent must be a multiple of 4");
-  DSC_REQUIRE(n2 >= 0 && n2 <= 32 && (n2 == 0 || (kv2 && n2 <= kv2_rows)), "dsc_star_mix_tc: bad h2 key count");
+  DSC_REQUIRE(n2 >= 0 && n2 <= 32 && (n2 == 0 || kv2), "dsc_star_mix_tc: bad h2 key count");
   DSC_REQUIRE(aligned16(att) && aligned16(x_tile) && aligned16(q_relay) && aligned16(att_relay) && aligned16(bias_o) &&
-              (!kv2 || aligned16(kv2)), "dsc_star_mix_tc: misaligned pointer");
+              aligned16(s_relay) && (!x_rowmajor || aligned16(x_rowmajor)) && (!kv2 || aligned16(kv2)), "dsc_star_mix_tc: misaligned pointer");
+  if (n2 == 0) kv2 = att;   // never dereferenced (lane < n2 is false); keeps the pointer arithmetic defined
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_mix_tc: prec must be 1 (bf16x3) or 2 (bf16)");
   if (n_sent == 0) return DSC_OK;
-  return prec == 1 ? launch_star_mix<3>(att, x_tile, packed_wo, packed_wkv_relay, bias_o, q_relay, kv2, kv2_rows, n2,
+  return prec == 1 ? launch_star_mix<3>(att, x_tile, x_rowmajor, s_relay, packed_wo, packed_wkv_relay, bias_o, q_relay, kv2, n2,
                                         att_relay, n_sent / 4, as_stream(stream))
-                   : launch_star_mix<1>(att, x_tile, packed_wo, packed_wkv_relay, bias_o, q_relay, kv2, kv2_rows, n2,
+                   : launch_star_mix<1>(att, x_tile, x_rowmajor, s_relay, packed_wo, packed_wkv_relay, bias_o, q_relay, kv2, n2,
                                         att_relay, n_sent / 4, as_stream(stream));
+}
+
+extern "C" int dsc_star_interleave(const float* src, int64_t src_group_stride, float* dst, int n_groups, int group_rows,
+                                   int width, void* stream) {
+  DSC_REQUIRE(src && dst && n_groups >= 0, "dsc_star_interleave: bad argument");
+  DSC_REQUIRE((group_rows == 128 || group_rows == 32) && width > 0 && (width % 32) == 0, "dsc_star_interleave: group_rows must be 128 or 32, width a multiple of 32");
+  DSC_REQUIRE(aligned16(src) && aligned16(dst) && (src_group_stride & 3) == 0, "dsc_star_interleave: misaligned pointer");
+  if (n_groups == 0) return DSC_OK;
+  dim3 grid(n_groups, width / 32);
+  if (group_rows == 128) interleave_kernel<128><<<grid, 256, 0, as_stream(stream)>>>(src, src_group_stride, dst, width);
+  else interleave_kernel<32><<<grid, 256, 0, as_stream(stream)>>>(src, src_group_stride, dst, width);
+  return check_launch("dsc_star_interleave");
+}
+
+extern "C" int dsc_star_kv2_put(const float* vals, float* kv2i, int row_index, int n_sent, void* stream) {
+  DSC_REQUIRE(vals && kv2i && row_index >= 0 && row_index < 32 && n_sent >= 0, "dsc_star_kv2_put: bad argument");
+  DSC_REQUIRE(aligned16(vals) && aligned16(kv2i), "dsc_star_kv2_put: misaligned pointer");
+  if (n_sent == 0) return DSC_OK;
+  kv2_put_kernel<<<(n_sent * 64 + 255) / 256, 256, 0, as_stream(stream)>>>(vals, kv2i, row_index, n_sent);
+  return check_launch("dsc_star_kv2_put");
 }

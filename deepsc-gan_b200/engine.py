@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .models import modules as M
-from .models.modules import StarWorkspace, star_cycles, _add_ln
+from .models.modules import StarWorkspace, prepare_kv_e, star_cycles, use_tc, _add_ln
 
 START_IDX = 1
 
@@ -48,6 +48,8 @@ class _StarLayerState:
         self.layer, self.relay, self.ln_a, self.ln_b = layer, relay, ln_a, ln_b
         self.kv_tar = torch.empty((n_sent, max_len, 256), **f)   # k|v of tar rows under multi_tar
         self.kv2 = torch.empty((n_sent, max_len, 256), **f)      # k|v of h2 rows under the relay weights
+        self.kv2i = torch.zeros((n_sent * 8192,), **f)           # same cache, interleaved (tcgen05 path)
+        self.kv2_row = torch.empty((n_sent, 256), **f)
         self.ws = StarWorkspace(n_sent, device)
         self.tile = torch.empty((n_sent, 32, 128), **f)
 
@@ -77,8 +79,8 @@ class StarGreedyDecoder:
         mem = net.channel_decoder.call(received)                      # hoisted out of the step loop
         st0 = self.layers[0]
         _lib.star_pack(mem.contiguous(), st0.tile)
-        _lib.linear(st0.tile.view(S * 32, 128), st0.layer.multi_att_satellite._packed("kv"), None, out=st0.ws.kv_e,
-                    prec=M.PREC)
+        prepare_kv_e(st0.tile, st0.layer.multi_att_satellite, st0.ws)
+        tc = use_tc(S)
         self.outputs.zero_()
         self.outputs[:, 0] = start_idx
         wf, bf = dec.final_layer.padded_kernel(), dec.final_layer.bias.detach()
@@ -92,11 +94,15 @@ class StarGreedyDecoder:
                 a = L.multi_tar.attend(q_t, st.kv_tar[:, :t + 1, 0:128], st.kv_tar[:, :t + 1, 128:256],
                                        key_ids=self.outputs)           # causal: the newest row sees the whole prefix
                 h2_t = _add_ln(a, x_t, L.layernorm1)
-                _lib.linear(h2_t.view(S, 128), st.relay._packed("kv"), None, out=st.kv2[:, t, :], prec=M.PREC)
+                if tc:
+                    _lib.linear(h2_t.view(S, 128), st.relay._packed("kv"), None, out=st.kv2_row, prec=M.PREC)
+                    _lib.star_kv2_put(st.kv2_row, st.kv2i, t)
+                else:
+                    _lib.linear(h2_t.view(S, 128), st.relay._packed("kv"), None, out=st.kv2[:, t, :], prec=M.PREC)
                 if li > 0:                                             # memory of layer li = output of layer li-1
                     _lib.star_pack(self.mid, st.tile)
                 x = star_cycles(st.tile, L.multi_att_satellite, st.relay, L.cycle_num, st.kv2, t + 1, st.ws,
-                                kv_e_ready=(li == 0))
+                                kv_e_ready=(li == 0), kv2i=st.kv2i if tc else None)
                 if li + 1 < len(self.layers):
                     _add_ln(x[:, :31], st.tile[:, :31], st.ln_a, st.ln_b, out=self.mid)
                 else:

@@ -199,38 +199,69 @@ class StarWorkspace:
         self.att = torch.empty((n_sent * 32, 128), **f)
         self.att_r = torch.empty((n_sent, 128), **f)
         self.q_r = torch.empty((n_sent, 128), **f)
+        self.s_buf = torch.empty((n_sent, 128), **f)        # relay nodes (tcgen05 path)
+        self.kvei = None                                    # interleaved k|v of the e rows (tcgen05 path)
+        self.kv2i = None                                    # interleaved h2 cache built from a row-major kv2
+
+    def tc_buffers(self):
+        if self.kvei is None:
+            f = dict(device=self.x.device, dtype=torch.float32)
+            self.kvei = torch.empty((self.n * 32 * 256,), **f)
+        return self.kvei
+
+
+def use_tc(n_sent: int) -> bool:
+    return PREC != 0 and n_sent % 4 == 0
+
+
+def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace) -> None:
+    """k|v of the e rows under the satellite weights (constant over cycles and greedy steps)."""
+    S = e_tile.shape[0]
+    _lib.linear(e_tile.view(S * 32, 128), sat._packed("kv"), None, out=ws.kv_e, prec=PREC)
+    if use_tc(S):
+        _lib.star_interleave(ws.kv_e.view(S // 4, 128, 256), ws.tc_buffers(), 128)
 
 
 def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_num: int,
                 kv2: Optional[torch.Tensor] = None, n2: int = 0, ws: Optional[StarWorkspace] = None,
-                kv_e_ready: bool = False) -> torch.Tensor:
+                kv_e_ready: bool = False, kv2i: Optional[torch.Tensor] = None) -> torch.Tensor:
     """The satellite/relay cycle loop of STE/STD/StarTransformer*Layer (models/modules.py:283-306,
     359-378) on star tiles, deduplicated: every node is projected once per cycle, neighbours are
     gathered by index.  e_tile [S,32,128] with row 31 = mean over tokens; returns the tile after
     ``cycle_num`` cycles (rows 0..30 = h, row 31 = s).  kv2 [S, rows, 256] holds k|v of h2 under the
-    relay weights (decoder only), of which the first n2 rows are attended."""
+    relay weights (decoder only), of which the first n2 rows are attended; ``kv2i`` is the same cache
+    already in the interleaved layout of the tcgen05 kernels."""
     S = e_tile.shape[0]
     if ws is None:
         ws = StarWorkspace(S, e_tile.device)
-    e2 = e_tile.view(S * 32, 128)
-    x2 = ws.x.view(S * 32, 128)
     if not kv_e_ready:
-        _lib.linear(e2, sat._packed("kv"), None, out=ws.kv_e, prec=PREC)
-    ws.x.copy_(e_tile)
-    s_rows = ws.x[:, 31, :]
-    if PREC != 0 and S % 4 == 0:
+        prepare_kv_e(e_tile, sat, ws)
+    if use_tc(S):
         # tcgen05 path: two fused persistent kernels per cycle (projection + satellite attention; dense + relay
-        # k|v projection + relay attention) and two per-sentence Dense calls for the relay node.
+        # k|v projection + relay attention) plus the two per-sentence Dense calls of the relay node.
+        if n2 > 0 and kv2i is None:
+            pad = torch.zeros((S, 32, 256), device=e_tile.device, dtype=torch.float32)
+            pad[:, : kv2.shape[1]] = kv2
+            kv2i = _lib.star_interleave(pad, torch.empty_like(pad).view(-1), 32)
         w_g, wo, bo = sat._packed("qkv_grouped"), sat.dense.kernel.detach(), sat.dense.bias.detach()
         wkv_r, wq_r = relay._packed("kv"), relay.wq.kernel.detach()
-        _lib.linear(s_rows, wq_r, None, out=ws.q_r, prec=PREC)
+        wo_r, bo_r = relay.dense.kernel.detach(), relay.dense.bias.detach()
+        xi, atti = ws.qkv.view(-1)[: S * 4096], ws.att.view(-1)           # reuse the unfused path's scratch
+        _lib.star_interleave(e_tile.view(S // 4, 128, 128), xi, 128)
+        ws.s_buf.copy_(e_tile[:, 31, :])
+        _lib.linear(ws.s_buf, wq_r, None, out=ws.q_r, prec=PREC)
         for c in range(cycle_num):
-            _lib.star_sat_tc(ws.x, ws.kv_e, w_g, ws.att, S, PREC)
-            _lib.star_mix_tc(ws.att, ws.x, wo, bo, wkv_r, ws.q_r, kv2, n2, ws.att_r, S, PREC)
-            _lib.linear(ws.att_r, relay.dense.kernel.detach(), relay.dense.bias.detach(), act=1, out=s_rows, prec=PREC)
-            if c + 1 < cycle_num:
-                _lib.linear(s_rows, wq_r, None, out=ws.q_r, prec=PREC)
+            last = c + 1 == cycle_num
+            _lib.star_sat_tc(xi, ws.s_buf, ws.kvei, w_g, atti, S, PREC)
+            _lib.star_mix_tc(atti, xi, ws.x if last else None, ws.s_buf, wo, bo, wkv_r, ws.q_r, kv2i, n2, ws.att_r, S, PREC)
+            _lib.linear(ws.att_r, wo_r, bo_r, act=1, out=ws.s_buf, prec=PREC)
+            if not last:
+                _lib.linear(ws.s_buf, wq_r, None, out=ws.q_r, prec=PREC)
+        ws.x[:, 31, :].copy_(ws.s_buf)
         return ws.x
+    x2 = ws.x.view(S * 32, 128)
+    ws.x.copy_(e_tile)
+    s_rows = ws.x[:, 31, :]
     w_qkv_s, w_qkv_r = sat._packed("qkv"), relay._packed("qkv")
     for _ in range(cycle_num):
         _lib.linear(x2, w_qkv_s, None, out=ws.qkv, prec=PREC)

@@ -92,20 +92,32 @@ int dsc_star_pack(const float* src, float* tile, int n_sent, void* stream);
  * {h[i+1], h[i], h[i-1], e[i], s} (cyclic neighbours, no mask); row 31 is zero-filled. */
 int dsc_star_satellite_attn(const float* qkv, const float* kv_e, float* att, int n_sent, void* stream);
 
-/* K2+K3 fused on tcgen05: att = satellite_attention(x_tile @ [wq|wk|wv]_satellite, kv_e) without materialising
- * the [rows,384] projection.  packed_wqkv_grouped = dsc_pack_weight of the [128,384] matrix whose columns are
- * ordered by head pair g = 0..3: [wq[:,32g:32g+32] | wk[:,32g:32g+32] | wv[:,32g:32g+32]].  n_sent % 4 == 0
- * (one persistent-CTA tile = 4 sentences = 128 TMEM lanes).  prec 1 = bf16x3, 2 = bf16. */
-int dsc_star_sat_tc(const float* x_tile, const float* kv_e, const void* packed_wqkv_grouped, float* att,
-                    int n_sent, int prec, void* stream);
+/* Fused tcgen05 star-cycle kernels (persistent CTAs, weights resident in shared memory, operand staged in TMEM).
+ * They stream per-row data in the "interleaved tile" layout [tile][k/4][row][4 floats] (a tile = 4 sentences = 128
+ * rows = 128 TMEM lanes) so that a warp's 32 rows read 512 contiguous bytes; dsc_star_interleave converts a
+ * row-major [n_groups*group_rows, width] tensor (group_rows 128, or 32 for the h2 cache) into it.  The relay node of
+ * each sentence lives in a compact buffer s_relay [n_sent,128] (row 31 of a tile is not stored).  n_sent % 4 == 0.
+ * prec 1 = bf16x3, 2 = bf16. */
+int dsc_star_interleave(const float* src, int64_t src_group_stride, float* dst, int n_groups, int group_rows,
+                        int width, void* stream);
+/* vals [n_sent,256] (k|v of one h2 row per sentence) -> row `row_index` of kv2 [n_sent][64][32][4]. */
+int dsc_star_kv2_put(const float* vals, float* kv2, int row_index, int n_sent, void* stream);
 
-/* K2+K4 fused on tcgen05: x_tile rows 0..30 <- relu(att @ wo_sat + bias_o) (row 31 keeps s), then
- * k|v = x_tile @ [wk|wv]_relay in TMEM and the relay attention of each sentence's query q_relay [n_sent,128]
- * (= s @ wq_relay) over its 32 tile rows plus the first n2 rows of kv2 [n_sent, kv2_rows, 256];
- * att_relay [n_sent,128] is the attention output before the relay dense layer.  packed_wo = dsc_pack_weight of
- * wo_sat [128,128], packed_wkv_relay of [wk|wv]_relay [128,256]. */
-int dsc_star_mix_tc(const float* att, float* x_tile, const void* packed_wo, const void* packed_wkv_relay,
-                    const float* bias_o, const float* q_relay, const float* kv2, int kv2_rows, int n2,
+/* K2+K3: att = satellite_attention(x @ [wq|wk|wv]_satellite, kv_e); the [rows,384] projection stays in TMEM
+ * (models/modules.py:289-299).  x_tile, att: [n_sent/4][32][128][4]; kv_e: [n_sent/4][64][128][4] (k|v of the e rows);
+ * packed_wqkv_grouped = dsc_pack_weight of the [128,384] matrix whose columns are ordered by head pair g = 0..3:
+ * [wq[:,32g:32g+32] | wk[:,32g:32g+32] | wv[:,32g:32g+32]]. */
+int dsc_star_sat_tc(const float* x_tile, const float* s_relay, const float* kv_e, const void* packed_wqkv_grouped,
+                    float* att, int n_sent, int prec, void* stream);
+
+/* K2+K4: x rows 0..30 <- relu(att @ wo_sat + bias_o) (models/modules.py:299), written to x_tile (interleaved) or,
+ * when x_rowmajor != NULL, to x_rowmajor [n_sent][32][128] with row 31 = s_relay (last cycle); then
+ * k|v = x @ [wk|wv]_relay in TMEM and the relay attention (:303-306, :375-378) of q_relay [n_sent,128] over the 32
+ * rows (31 satellites + s) plus the first n2 rows of kv2 [n_sent][64][32][4]; att_relay [n_sent,128] is the output
+ * before the relay dense layer.  packed_wo / packed_wkv_relay = dsc_pack_weight of [128,128] / [128,256]. */
+int dsc_star_mix_tc(const float* att, float* x_tile, float* x_rowmajor, const float* s_relay,
+                    const void* packed_wo, const void* packed_wkv_relay,
+                    const float* bias_o, const float* q_relay, const float* kv2, int n2,
                     float* att_relay, int n_sent, int prec, void* stream);
 
 /* K4: relay attention of one star cycle (models/modules.py:303-306, 375-378).

@@ -341,7 +341,8 @@ def test_linear_tensor_core_row_skip_strided(L, dev):
 @pytest.mark.parametrize("prec,tol", [(1, 1e-4), (2, 5e-2)])
 @pytest.mark.parametrize("S", [4, 600, 2368])
 def test_star_sat_fused_matches_unfused(L, dev, S, prec, tol):
-    """dsc_star_sat_tc (UMMA projection + shuffle attention) == dsc_linear(fp32) + dsc_star_satellite_attn."""
+    """dsc_star_sat_tc (UMMA projection + shuffle attention on interleaved tiles) == dsc_linear(fp32) +
+    dsc_star_satellite_attn on row-major tiles."""
     import deepsc_gan_b200.models.modules as M
     g = torch.Generator().manual_seed(S)
     sat = M.sublayer1(128, 8).to(dev)
@@ -353,7 +354,24 @@ def test_star_sat_fused_matches_unfused(L, dev, S, prec, tol):
     qkv = L.linear(x.view(S * 32, 128), sat._packed("qkv"), None)
     ref = torch.empty(S * 32, 128, device=dev)
     L.star_satellite_attn(qkv, kv_e, ref, S)
-    got = torch.full((S * 32, 128), 5.0, device=dev)
-    L.star_sat_tc(x, kv_e, sat._packed("qkv_grouped"), got, S, prec)
+    xi = L.star_interleave(x.view(S // 4, 128, 128), torch.empty(S * 4096, device=dev), 128)
+    kvei = L.star_interleave(kv_e.view(S // 4, 128, 256), torch.empty(S * 8192, device=dev), 128)
+    atti = torch.full((S * 4096,), 5.0, device=dev)
+    L.star_sat_tc(xi, x[:, 31, :].contiguous(), kvei, sat._packed("qkv_grouped"), atti, S, prec)
     torch.cuda.synchronize()
+    got = atti.view(S // 4, 32, 128, 4).permute(0, 2, 1, 3).reshape(S * 32, 128)      # undo the interleave
     assert rel_err(got, ref) < tol
+
+
+def test_star_interleave_layout(L, dev):
+    g = torch.Generator().manual_seed(0)
+    for R, W in ((128, 128), (128, 256), (32, 256)):
+        src = torch.randn(3, R, W, generator=g).to(dev)
+        dst = L.star_interleave(src, torch.empty(src.numel(), device=dev), R)
+        want = src.view(3, R, W // 4, 4).permute(0, 2, 1, 3).reshape(-1)
+        assert torch.equal(dst, want)
+    kv2i = torch.zeros(5 * 8192, device=dev)
+    vals = torch.randn(5, 256, generator=g).to(dev)
+    L.star_kv2_put(vals, kv2i, 7)
+    assert torch.equal(kv2i.view(5, 64, 32, 4)[:, :, 7, :].reshape(5, 256), vals)
+    assert float(kv2i.view(5, 64, 32, 4)[:, :, 8, :].abs().max()) == 0.0
