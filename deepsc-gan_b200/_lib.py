@@ -35,6 +35,7 @@ _SIGNATURES = {
     "dsc_star_interleave": (C.c_int, [vp, i64, vp, i32, i32, i32, vp]),
     "dsc_star_kv2_put": (C.c_int, [vp, vp, i32, i32, vp]),
     "dsc_star_mix_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
+    "dsc_star_relay_update": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp]),
     "dsc_star_relay_attn": (C.c_int, [vp, vp, i32, i32, vp, i32, vp]),
     "dsc_mha_attention": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,
                                     i32, i32, i32, vp]),
@@ -253,6 +254,16 @@ def star_mix_tc(atti: torch.Tensor, xi: torch.Tensor, x_rowmajor: Optional[torch
                                   bias_o.data_ptr(), q_relay.data_ptr(), _ptr(kv2i), n2, att_relay.data_ptr(), n_sent,
                                   prec, _stream()), "dsc_star_mix_tc")
     return att_relay
+
+
+def star_relay_update(att_r: torch.Tensor, wo: torch.Tensor, bo: torch.Tensor, wq: torch.Tensor, s_out: torch.Tensor,
+                      q_out: torch.Tensor) -> None:
+    """s_out = relu(att_r @ wo + bo); q_out = s_out @ wq (fp32)."""
+    _need_cuda(att_r, wo, bo, wq, s_out, q_out)
+    for t in (att_r, wo, wq, s_out, q_out):
+        assert t.is_contiguous()
+    _check(load().dsc_star_relay_update(att_r.data_ptr(), wo.data_ptr(), bo.data_ptr(), wq.data_ptr(), s_out.data_ptr(),
+                                        q_out.data_ptr(), att_r.shape[0], _stream()), "dsc_star_relay_update")
 
 
 def star_relay_attn(qkv_r: torch.Tensor, kv2: Optional[torch.Tensor], n2: int, out: torch.Tensor, n_sent: int):

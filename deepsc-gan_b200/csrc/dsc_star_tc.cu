@@ -25,7 +25,7 @@ namespace dsc {
 using namespace tc;
 
 // TMEM column map (512 columns allocated)
-constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_A_HI = 256, COL_A_LO = 320;       // satellite kernel
+constexpr uint32_t COL_ACC0 = 0, COL_ACC1 = 128, COL_A_HI = 256, COL_A_LO = 320, COL_KVE0 = 384, COL_KVE1 = 448;   // satellite kernel
 constexpr uint32_t MIX_ACC_O = 0, MIX_ACC_KV = 128, MIX_A_HI = 384, MIX_A_LO = 448;     // mix kernel
 constexpr int kLoaderWarps = 8, kEpiWarps = 8;
 constexpr int kThreads = (kLoaderWarps + kEpiWarps + 1) * 32;      // 544
@@ -42,6 +42,10 @@ struct Bars {
   uint64_t kv_free;         // mix kernel: K|V accumulators drained
   uint64_t o_full;          // mix kernel: dense (Wo) accumulators ready
   uint64_t o_free;          // mix kernel: dense accumulators drained
+  uint64_t kve_full[2];     // satellite kernel: e-key slot staged in TMEM by the loader warps
+  uint64_t kve_free[2];     // satellite kernel: e-key slot consumed by the epilogue warps
+  uint64_t h2_full;         // mix kernel: h2-key partial softmax published by the loader warps
+  uint64_t h2_free;         // mix kernel: partials consumed by the epilogue warps
 };
 
 // stage one half row (64 fp32 -> 32 hi + 32 lo packed words) into the thread's TMEM lane
@@ -91,7 +95,7 @@ __device__ __forceinline__ void issue_group(uint32_t tmem_base, uint32_t acc_col
 template <int NPASS>
 __global__ void __launch_bounds__(kThreads, 1)
 star_sat_kernel(const float* __restrict__ XI, const float* __restrict__ Sbuf, const float* __restrict__ KVEI,
-                const uint8_t* __restrict__ wblob, float* __restrict__ ATTI, int n_tiles) {
+                const uint8_t* __restrict__ wblob, float* __restrict__ ATTI, int n_tiles, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sW = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) Bars bars;
@@ -104,7 +108,10 @@ star_sat_kernel(const float* __restrict__ XI, const float* __restrict__ Sbuf, co
     mbar_init(&bars.w_full, 1);
     mbar_init(&bars.a_full, kLoaderWarps * 32);
     mbar_init(&bars.a_free, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kEpiWarps * 32); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kEpiWarps * 32);
+      mbar_init(&bars.kve_full[b], kLoaderWarps * 32); mbar_init(&bars.kve_free[b], kEpiWarps * 32);
+    }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(&tmem_base_s);
@@ -118,18 +125,52 @@ star_sat_kernel(const float* __restrict__ XI, const float* __restrict__ Sbuf, co
     const int quarter = warp & 3, half = warp >> 2;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int row_in_tile = quarter * 32 + lane;
+    // Each loader thread also stages the e-keys of its row for head `2g + half` into a TMEM slot (double
+    // buffered over the head pairs g), so that the epilogue warps never wait on an HBM load.
     uint32_t hi[32], lo[32];
-    int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    uint32_t kv[32];                                              // k[16] | v[16] of (row, head) as raw fp32 bits
+    auto load_kve = [&](int t, int g) {
+      const uint4* base = reinterpret_cast<const uint4*>(KVEI + (int64_t)t * 32768) + row_in_tile;
+      const int head = 2 * g + half;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 a = __ldg(base + (head * 4 + q) * 128), c = __ldg(base + (32 + head * 4 + q) * 128);
+        kv[4*q] = a.x; kv[4*q+1] = a.y; kv[4*q+2] = a.z; kv[4*q+3] = a.w;
+        kv[16+4*q] = c.x; kv[16+4*q+1] = c.y; kv[16+4*q+2] = c.z; kv[16+4*q+3] = c.w;
+      }
+    };
+    auto load_x = [&](int t) {
       if (lane == 31)   // relay row: compact buffer S[sentence][128]
         load_half_row(reinterpret_cast<const float4*>(Sbuf + ((int64_t)t * 4 + quarter) * 128 + half * 64), 1, hi, lo);
       else
         load_half_row(reinterpret_cast<const float4*>(XI + (int64_t)t * 16384) + (half * 16) * 128 + row_in_tile, 128, hi, lo);
+    };
+    // Register budget (96/thread): the operand registers (hi/lo, 64) and the e-key registers (32) are never live
+    // together - X(t+1) is fetched after the last e-key slot of tile t is staged, the e-keys of (t, 0) right
+    // after the operand of tile t is in TMEM.
+    int it = 0;
+    if ((int)blockIdx.x < n_tiles) load_x(blockIdx.x);
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       mbar_wait(&bars.a_free, (it - 1) & 1);                       // previous tile's UMMAs are done with the operand
       tc_fence_after();
       store_half_row<NPASS>(lane_addr, COL_A_HI, COL_A_LO, half, hi, lo);
       tc_fence_before();
       mbar_arrive(&bars.a_full);
+      if (!(dbg & 2)) load_kve(t, 0);
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        const int b = g & 1, use = it * 2 + (g >> 1);
+        mbar_wait(&bars.kve_free[b], (use - 1) & 1);
+        tc_fence_after();
+        const uint32_t slot = lane_addr + (b ? COL_KVE1 : COL_KVE0);
+        tmem_st16(slot + half * 16, kv);
+        tmem_st16(slot + 32 + half * 16, kv + 16);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.kve_full[b]);
+        if (g < 3 && !(dbg & 2)) load_kve(t, g + 1);
+      }
+      if (t + (int)gridDim.x < n_tiles) load_x(t + gridDim.x);     // next tile's operand
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ UMMA issuer
@@ -147,7 +188,7 @@ star_sat_kernel(const float* __restrict__ XI, const float* __restrict__ Sbuf, co
           const int b = g & 1, use = it * 2 + (g >> 1);
           mbar_wait(&bars.acc_free[b], (use - 1) & 1);
           tc_fence_after();
-          issue_group<NPASS, 96>(tmem_base, b ? COL_ACC1 : COL_ACC0, COL_A_HI, COL_A_LO, b_base, W_PLANE, (uint32_t)g * 96u);
+          if (!(dbg & 4)) issue_group<NPASS, 96>(tmem_base, b ? COL_ACC1 : COL_ACC0, COL_A_HI, COL_A_LO, b_base, W_PLANE, (uint32_t)g * 96u);
           umma_commit(&bars.acc_full[b]);
         }
         umma_commit(&bars.a_free);
@@ -164,51 +205,53 @@ star_sat_kernel(const float* __restrict__ XI, const float* __restrict__ Sbuf, co
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int row_in_tile = quarter * 32 + lane;
-      const float4* kve = reinterpret_cast<const float4*>(KVEI + (int64_t)t * 32768) + row_in_tile;
       float4* att = reinterpret_cast<float4*>(ATTI + (int64_t)t * 16384) + row_in_tile;
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
         const int b = g & 1, use = it * 2 + (g >> 1);
         const int head = g * 2 + hh;
-        // e-keys of this row/head (constant over cycles) - issue before waiting on the accumulators
-        float ke[16], ve[16];
-        {
-          const float4* kp = kve + (head * 4) * 128;
-          const float4* vp = kve + (32 + head * 4) * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 a = __ldg(kp + q * 128), c = __ldg(vp + q * 128);
-            ke[4*q] = a.x; ke[4*q+1] = a.y; ke[4*q+2] = a.z; ke[4*q+3] = a.w;
-            ve[4*q] = c.x; ve[4*q+1] = c.y; ve[4*q+2] = c.z; ve[4*q+3] = c.w;
-          }
-        }
+        mbar_wait(&bars.kve_full[b], use & 1);                     // e-keys of this row/head, staged by the loaders
         mbar_wait(&bars.acc_full[b], use & 1);
         tc_fence_after();
-        float q[16], k[16], v[16];
         const uint32_t col = lane_addr + (b ? COL_ACC1 : COL_ACC0) + hh * 16;
-        tmem_ld16(col, q);
-        tmem_ld16(col + 32, k);
-        tmem_ld16(col + 64, v);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&bars.acc_free[b]);
+        const uint32_t kcol = lane_addr + (b ? COL_KVE1 : COL_KVE0) + hh * 16;
         float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
-#pragma unroll
-        for (int d = 0; d < 16; ++d) {
-          const float ku = __shfl_sync(0xffffffffu, k[d], up);
-          const float kd = __shfl_sync(0xffffffffu, k[d], dn);
-          const float ks = __shfl_sync(0xffffffffu, k[d], 31);
-          l0 = fmaf(q[d], ku, l0);
-          l1 = fmaf(q[d], k[d], l1);
-          l2 = fmaf(q[d], kd, l2);
-          l3 = fmaf(q[d], ke[d], l3);
-          l4 = fmaf(q[d], ks, l4);
+        if (dbg & 1) {
+          tc_fence_before();
+          mbar_arrive(&bars.acc_free[b]);
+          mbar_arrive(&bars.kve_free[b]);
+          continue;
         }
+        {
+          float q[16], k[16], ke[16];
+          tmem_ld16(col, q);
+          tmem_ld16(col + 32, k);
+          tmem_ld16(kcol, ke);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) {
+            const float ku = __shfl_sync(0xffffffffu, k[d], up);
+            const float kd = __shfl_sync(0xffffffffu, k[d], dn);
+            const float ks = __shfl_sync(0xffffffffu, k[d], 31);
+            l0 = fmaf(q[d], ku, l0);
+            l1 = fmaf(q[d], k[d], l1);
+            l2 = fmaf(q[d], kd, l2);
+            l3 = fmaf(q[d], ke[d], l3);
+            l4 = fmaf(q[d], ks, l4);
+          }
+        }
+        float v[16], ve[16];
+        tmem_ld16(col + 64, v);
+        tmem_ld16(kcol + 32, ve);
         l0 *= 0.25f; l1 *= 0.25f; l2 *= 0.25f; l3 *= 0.25f; l4 *= 0.25f;
         const float mx = fmaxf(fmaxf(fmaxf(l0, l1), fmaxf(l2, l3)), l4);
         l0 = expf(l0 - mx); l1 = expf(l1 - mx); l2 = expf(l2 - mx); l3 = expf(l3 - mx); l4 = expf(l4 - mx);
         const float inv = 1.0f / (l0 + l1 + l2 + l3 + l4);
         l0 *= inv; l1 *= inv; l2 *= inv; l3 *= inv; l4 *= inv;
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.acc_free[b]);
+        mbar_arrive(&bars.kve_free[b]);
         float o[16];
 #pragma unroll
         for (int d = 0; d < 16; ++d) {
@@ -463,12 +506,12 @@ kv2_put_kernel(const float* __restrict__ vals, float* __restrict__ kv2i, int row
 using namespace dsc;
 
 template <int NPASS>
-static int launch_star_sat(const float* x, const float* sbuf, const float* kv_e, const void* w, float* att, int n_tiles, cudaStream_t s) {
+static int launch_star_sat(const float* x, const float* sbuf, const float* kv_e, const void* w, float* att, int n_tiles, int dbg, cudaStream_t s) {
   constexpr size_t smem = (size_t)(NPASS == 3 ? 4 : 2) * 384 * 128 + 1024;
   cudaError_t e = cudaFuncSetAttribute(star_sat_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("dsc_star_sat_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
   int grid = n_tiles < kSMs ? n_tiles : kSMs;
-  star_sat_kernel<NPASS><<<grid, kThreads, smem, s>>>(x, sbuf, kv_e, reinterpret_cast<const uint8_t*>(w), att, n_tiles);
+  star_sat_kernel<NPASS><<<grid, kThreads, smem, s>>>(x, sbuf, kv_e, reinterpret_cast<const uint8_t*>(w), att, n_tiles, dbg);
   return check_launch("dsc_star_sat_tc");
 }
 
@@ -478,10 +521,12 @@ extern "C" int dsc_star_sat_tc(const float* x_tile, const float* s_relay, const 
   DSC_REQUIRE(n_sent >= 0 && (n_sent % 4) == 0, "dsc_star_sat_tc: n_sent must be a multiple of 4 (one tile = 4 sentences)");
   DSC_REQUIRE(aligned16(x_tile) && aligned16(kv_e) && aligned16(att) && ((uintptr_t)packed_wqkv_grouped & 127u) == 0,
               "dsc_star_sat_tc: misaligned pointer");
+  const int dbg = prec >> 8;                    // profiling knobs (tools/time_star.py): 1 no attention math, 2 no e-key loads, 4 no UMMA
+  prec &= 255;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_sat_tc: prec must be 1 (bf16x3) or 2 (bf16)");
   if (n_sent == 0) return DSC_OK;
-  return prec == 1 ? launch_star_sat<3>(x_tile, s_relay, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream))
-                   : launch_star_sat<1>(x_tile, s_relay, kv_e, packed_wqkv_grouped, att, n_sent / 4, as_stream(stream));
+  return prec == 1 ? launch_star_sat<3>(x_tile, s_relay, kv_e, packed_wqkv_grouped, att, n_sent / 4, dbg, as_stream(stream))
+                   : launch_star_sat<1>(x_tile, s_relay, kv_e, packed_wqkv_grouped, att, n_sent / 4, dbg, as_stream(stream));
 }
 
 template <int NPASS>

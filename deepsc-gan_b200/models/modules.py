@@ -254,9 +254,7 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
             last = c + 1 == cycle_num
             _lib.star_sat_tc(xi, ws.s_buf, ws.kvei, w_g, atti, S, PREC)
             _lib.star_mix_tc(atti, xi, ws.x if last else None, ws.s_buf, wo, bo, wkv_r, ws.q_r, kv2i, n2, ws.att_r, S, PREC)
-            _lib.linear(ws.att_r, wo_r, bo_r, act=1, out=ws.s_buf, prec=PREC)
-            if not last:
-                _lib.linear(ws.s_buf, wq_r, None, out=ws.q_r, prec=PREC)
+            _lib.star_relay_update(ws.att_r, wo_r, bo_r, wq_r, ws.s_buf, ws.q_r)
         ws.x[:, 31, :].copy_(ws.s_buf)
         return ws.x
     x2 = ws.x.view(S * 32, 128)

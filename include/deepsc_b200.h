@@ -120,6 +120,11 @@ int dsc_star_mix_tc(const float* att, float* x_tile, float* x_rowmajor, const fl
                     const float* bias_o, const float* q_relay, const float* kv2, int n2,
                     float* att_relay, int n_sent, int prec, void* stream);
 
+/* relay node update: s_out = relu(att_relay @ wo + bo) (models/modules.py:305-306), q_out = s_out @ wq (the next
+ * cycle's relay query).  fp32 FFMA, weights Keras layout [128,128] contiguous, all tensors [n_sent,128]. */
+int dsc_star_relay_update(const float* att_relay, const float* wo, const float* bo, const float* wq,
+                          float* s_out, float* q_out, int n_sent, void* stream);
+
 /* K4: relay attention of one star cycle (models/modules.py:303-306, 375-378).
  * qkv_r [n_sent*32, 384] = updated tile @ [wq|wk|wv] of the relay weights; the query is row 31,
  * keys/values are row 31 (s), rows 0..30 (h) and, for the decoder, the first n2 rows of

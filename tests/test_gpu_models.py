@@ -93,6 +93,32 @@ def test_forward_and_greedy_against_goldens(dev, kind, channel):
     assert np.array_equal(counts, B.bleu_counts(gold["inp"], ids_c.numpy()))
 
 
+@pytest.mark.parametrize("kind", ["Transeiver_Star", "Transeiver_star", "Transeiver"])
+def test_tensor_core_precision_mode(dev, kind, monkeypatch):
+    """prec=1 (tcgen05, bf16x3 split, fused star-cycle kernels): logits within 1e-3 relative of the oracle, greedy ids
+    identical except where the oracle's own fp64 top-2 margin is a numerical tie."""
+    import deepsc_gan_b200.models.modules as M0
+    from deepsc_gan_b200.models.modules import create_masks
+    from deepsc_gan_b200.utlis.eval import greedy_decode_noattack
+    monkeypatch.setattr(M0, "PREC", 1)
+    gold = np.load(_cases.golden_path(kind, "AWGN"))
+    args, net = build(kind, dev)
+    inp = torch.from_numpy(gold["inp"]).to(dev)
+    z, z_r, p, h_z, h_z_r = _cases.draws()
+    n_std = O.snr_to_noise(_cases.SNR_DB)
+    tar_inp = inp[:, :-1]
+    masks = create_masks(inp, tar_inp)
+    with torch.no_grad():
+        pred, x, y, _ = net(inp, tar_inp, p.to(dev), 3.0, "AWGN", n_std, False, *masks, noise=z.to(dev), h=h_z)
+    assert rel_err(x[:8], gold["symbols"]) < RTOL
+    assert rel_err(pred[:4, :, :64], gold["logits_slice"]) < RTOL
+    assert rel_err(torch.logsumexp(pred, -1), gold["lse"]) < RTOL
+    ids = greedy_decode_noattack(args, inp, net, 0.0, "AWGN", n_std, noise=z.to(dev), h=h_z).cpu()
+    n_bad, unexplained = explained_mismatches(kind, "AWGN", ids, torch.from_numpy(gold["greedy_ids"]), inp.cpu())
+    assert unexplained == 0, f"{unexplained} sentences differ from the oracle beyond a numerical tie"
+    assert n_bad <= 3, f"{n_bad} sentences hit ties"
+
+
 def test_multi_unit_greedy_equals_per_unit_oracle(dev):
     """Three units at three SNR points in one set of launches == the oracle run unit by unit."""
     from deepsc_gan_b200 import engine
