@@ -5,15 +5,15 @@
 
 Workload (BASELINE.json configs[1]): Star-Transformer DeepSC-GAN (`Transeiver_Star`, SE/SD, cycle_num 8)
 over AWGN, SNR sweep 0..18 dB, greedy argmax decode of 30 steps, BLEU n-gram counts.  One "step" = one pass of
-the path over a batch of U 64-sentence synthetic Europarl-shape units (U = 38 by default: every SNR point of the
-sweep twice), weights random-init (the reference's checkpoints are missing).  One "sentence" = one sentence
+the path over a batch of U 64-sentence synthetic Europarl-shape units (U = 37 by default = 592 four-sentence tiles = 4 x 148 SMs; SNR points of the
+sweep are dealt round-robin), weights random-init (the reference's checkpoints are missing).  One "sentence" = one sentence
 evaluated at one SNR point.  N > 1: each rank processes its own U units (weak scaling, no data-path collective);
 the int32 BLEU count table is all-gathered at the end of every step.
 
 value   : inputs resident in HBM, CUDA-event time, max over ranks.
 e2e     : same metric through the public API with HOST buffers: per step the ids are copied from pinned host
           memory and the BLEU counts are read back, both inside the timed region.
-roofline: the dominant kernel (the Dense GEMM of the star cycles), FLOPs per launch / mean event-timed launch.
+roofline: the dominant kernel (star_sat_kernel, HBM-bound per-cycle launch), algorithmic bytes per launch / mean event-timed launch.
 cpu_baseline / --impl reference: the CPU oracle (PyTorch restatement of the reference; the TensorFlow reference
           itself cannot run here) on a bounded sample of the same workload, all host threads.
 """
@@ -36,6 +36,9 @@ import torch
 METRIC = "sentences/sec for SNR-sweep encode->channel->decode+BLEU"
 UNIT = "sentences/s"
 SNRS = list(range(19))
+# dram__bytes_read.sum + dram__bytes_write.sum of one star_sat_kernel<3> launch from the `ncu --set full` capture
+# summarised in profiles/ (keyed by sentences per launch); null when no capture exists for the size that ran
+ROOFLINE_TRAFFIC_BYTES = {2368: 117852416 + 19215872}
 
 
 def load_peaks():
@@ -137,10 +140,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--units", type=int, default=38, help="64-sentence units per step per GPU")
+    ap.add_argument("--units", type=int, default=37, help="64-sentence units per step per GPU")
     ap.add_argument("--ref-units", type=int, default=4, help="units per step of the CPU reference arm")
     ap.add_argument("--cpu-units", type=int, default=8, help="units of the cpu_baseline sample (N=1 only)")
-    ap.add_argument("--prec", type=int, default=0, help="0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16")
+    ap.add_argument("--prec", type=int, default=1, help="0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -227,21 +230,25 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms, t_e2e_ms = float(tt[0]), float(tt[1])
 
-    # ---- roofline of the dominant kernel: the [S*32,128] x [128,384] projection GEMM of the star cycles ------
-    dom = [(a.elapsed_time(b), M, K, N) for a, b, M, K, N in prof if K == 128 and N == 384 and M == S * 32]
-    allg = [(a.elapsed_time(b), M, K, N) for a, b, M, K, N in prof]
-    gemm_ms = sum(t for t, *_ in allg)
+    # ---- roofline of the dominant kernel: star_sat_kernel (fused QKV projection + satellite attention) ----------
+    # HBM-bound as launched per cycle: per sentence it reads the 31 node rows + relay row (32 x 512 B), the k|v of the
+    # 31 e rows (31 x 1024 B) and writes 31 attention rows (31 x 512 B) = 64,000 algorithmic bytes.
+    SAT_BYTES_PER_SENTENCE = 32 * 512 + 31 * 1024 + 31 * 512
+    dom = [(a.elapsed_time(b), meta) for op, a, b, meta in prof if op == "dsc_star_sat_tc" and meta == S]
     roof = None
     if dom:
-        mean_ms = sum(t for t, *_ in dom) / len(dom)
-        flops = 2.0 * S * 32 * 128 * 384
-        achieved = flops / (mean_ms * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": "dsc_linear [S*32,128]x[128,384] (star-cycle QKV projection)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
-                "launches_timed": len(dom), "mean_launch_ms": mean_ms, "flops_per_launch": flops,
-                "gemm_share_of_step": gemm_ms / t_ms, "arith": {0: "fp32 FFMA", 1: "bf16x3 tcgen05", 2: "bf16 tcgen05"}[args.prec]}
+        mean_ms = sum(t for t, _ in dom) / len(dom)
+        nbytes = float(SAT_BYTES_PER_SENTENCE) * S
+        achieved = nbytes / (mean_ms * 1e-3) / 1e9
+        peak = peaks["hbm_gbs"]
+        roof = {"bound": "hbm", "kernel": "star_sat_kernel<3> via dsc_star_sat_tc (QKV projection on tcgen05 + satellite "
+                                          "attention, one launch per star cycle)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ROOFLINE_TRAFFIC_BYTES.get(S),
+                "peak_source": f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
+                "launches_timed": len(dom), "mean_launch_ms": mean_ms, "bytes_per_launch": nbytes,
+                "share_of_step": sum(t for t, _ in dom) / t_ms,
+                "arith": {1: "bf16x3 tcgen05, fp32 accumulate/softmax", 2: "bf16 tcgen05"}.get(args.prec, "fp32")}
 
     if rank != 0:
         if world > 1:

@@ -76,8 +76,29 @@ class DscError(RuntimeError):
 # kernel launches issued through this binding (bench.py reports them as gpu_launches)
 _KERNELS_PER_CALL = {"dsc_vocab_argmax": 2}
 STATS = {"launches": 0}
-# when set to a list, linear() appends (start_event, end_event, M, K, N) for roofline accounting
+# when set to a list, the wrappers named in PROFILE_OPS append (op, start_event, end_event, meta) for bench.py's
+# roofline accounting (CUDA events on the launching stream around the single kernel launch)
 PROFILE = None
+PROFILE_OPS = ("dsc_star_sat_tc",)
+
+
+class _timed:
+    """with _timed("dsc_x", meta): launch  -> PROFILE.append(("dsc_x", ev0, ev1, meta)) when profiling is on."""
+
+    def __init__(self, op: str, meta):
+        self.on = PROFILE is not None and op in PROFILE_OPS
+        self.op, self.meta = op, meta
+
+    def __enter__(self):
+        if self.on:
+            self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ev1.record()
+            PROFILE.append((self.op, self.ev0, self.ev1, self.meta))
+        return False
 
 
 def _check(rc: int, what: str) -> None:
@@ -158,20 +179,17 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     if out is None:
         out = torch.empty((M, N), device=x.device, dtype=torch.float32)
     assert out.dim() == 2 and out.shape[0] == M and out.shape[1] == N and out.stride(1) == 1
-    if PROFILE is not None:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
     if prec != 0 and K % 128 == 0:
         blob = packed_weight(w, N)
-        _check(load().dsc_linear_tc(_f32(x).data_ptr(), x.stride(0), blob.data_ptr(), _ptr(bias), out.data_ptr(),
-                                    out.stride(0), M, K, N, act, row_mod, row_skip, prec, _stream()), "dsc_linear_tc")
+        with _timed("dsc_linear_tc", (M, K, N)):
+            _check(load().dsc_linear_tc(_f32(x).data_ptr(), x.stride(0), blob.data_ptr(), _ptr(bias), out.data_ptr(),
+                                        out.stride(0), M, K, N, act, row_mod, row_skip, prec, _stream()),
+                   "dsc_linear_tc")
     else:
-        _check(load().dsc_linear(_f32(x).data_ptr(), x.stride(0), _f32(w).data_ptr(), w.stride(0), _ptr(bias),
-                                 out.data_ptr(), out.stride(0), M, K, N, act, row_mod, row_skip, 0, _stream()),
-               "dsc_linear")
-    if PROFILE is not None:
-        ev1.record()
-        PROFILE.append((ev0, ev1, M, K, N))
+        with _timed("dsc_linear", (M, K, N)):
+            _check(load().dsc_linear(_f32(x).data_ptr(), x.stride(0), _f32(w).data_ptr(), w.stride(0), _ptr(bias),
+                                     out.data_ptr(), out.stride(0), M, K, N, act, row_mod, row_skip, 0, _stream()),
+                   "dsc_linear")
     return out
 
 
@@ -235,8 +253,9 @@ def star_sat_tc(xi: torch.Tensor, s_relay: torch.Tensor, kvei: torch.Tensor, w_g
     _need_cuda(xi, s_relay, kvei, w_grouped, atti)
     assert xi.is_contiguous() and kvei.is_contiguous() and atti.is_contiguous() and s_relay.is_contiguous()
     blob = packed_weight(w_grouped, 384)
-    _check(load().dsc_star_sat_tc(xi.data_ptr(), s_relay.data_ptr(), kvei.data_ptr(), blob.data_ptr(), atti.data_ptr(),
-                                  n_sent, prec, _stream()), "dsc_star_sat_tc")
+    with _timed("dsc_star_sat_tc", n_sent):
+        _check(load().dsc_star_sat_tc(xi.data_ptr(), s_relay.data_ptr(), kvei.data_ptr(), blob.data_ptr(),
+                                      atti.data_ptr(), n_sent, prec, _stream()), "dsc_star_sat_tc")
     return atti
 
 
