@@ -44,6 +44,8 @@ _SIGNATURES = {
     "dsc_channel": (C.c_int, [vp, vp, f32, vp, u64, u64, vp, vp, f32, vp, vp, vp, i32, vp, vp, i32, i64, vp]),
     "dsc_vocab_argmax": (C.c_int, [vp, i64, vp, i64, vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp]),
     "dsc_vocab_argmax_workspace": (C.c_int64, [i32, i32]),
+    "dsc_vocab_argmax_tc_workspace": (C.c_int64, [i32, i32]),
+    "dsc_vocab_argmax_tc": (C.c_int, [vp, i64, vp, vp, vp, i64, vp, i64, i32, i32, i32, vp]),
     "dsc_argmax_rows": (C.c_int, [vp, i64, vp, i64, i32, i32, vp]),
     "dsc_masked_ce_rows": (C.c_int, [vp, i64, vp, vp, i32, i32, vp]),
     "dsc_bleu_counts": (C.c_int, [vp, i32, vp, i32, vp, i32, vp]),
@@ -366,6 +368,19 @@ def channel(x: torch.Tensor, n_units: int, n_std: torch.Tensor, *, x_sumsq=None,
     return y, xn
 
 
+_VOCAB_WS = {}
+
+
+def _vocab_tc_workspace(M: int, n_vocab: int, device) -> torch.Tensor:
+    """Zero-filled once; the kernel's arrival counters reset themselves, calls on one stream are ordered."""
+    key = (M, n_vocab, torch.device(device).index, torch.cuda.current_stream().cuda_stream)
+    ws = _VOCAB_WS.get(key)
+    if ws is None:
+        ws = torch.zeros((load().dsc_vocab_argmax_tc_workspace(M, n_vocab),), device=device, dtype=torch.uint8)
+        _VOCAB_WS[key] = ws
+    return ws
+
+
 def vocab_argmax(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n_vocab: int, ids_out: torch.Tensor,
                  logits: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
                  prec: int = 0) -> torch.Tensor:
@@ -378,15 +393,22 @@ def vocab_argmax(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n_vocab: 
     if logits is not None:
         assert logits.dim() == 2 and logits.shape == (M, n_vocab) and logits.stride(1) == 1
         ld_logits = logits.stride(0)
-    elif workspace is None:
+    elif workspace is None and prec == 0:
         workspace = torch.empty((load().dsc_vocab_argmax_workspace(M, n_vocab),), device=x.device,
                                 dtype=torch.float32)
+    if prec != 0 and logits is None:
+        # fused tcgen05 projection + running argmax: the logits never reach HBM
+        ws = _vocab_tc_workspace(M, n_vocab, x.device)
+        with _timed("dsc_vocab_argmax_tc", (M, n_vocab)):
+            _check(load().dsc_vocab_argmax_tc(_f32(x).data_ptr(), x.stride(0), packed_weight(w, n_vocab).data_ptr(),
+                                              bias.data_ptr(), ids_out.data_ptr(), ids_out.stride(0) if M > 1 else 1,
+                                              ws.data_ptr(), ws.numel(), M, n_vocab, prec, _stream()),
+                   "dsc_vocab_argmax_tc")
+        return ids_out
     if prec != 0:
-        # tensor-core projection into the (caller-provided) logits/workspace rows, then the row argmax kernel
-        ld = (n_vocab + 3) // 4 * 4
-        lg = logits if logits is not None else workspace[: M * ld].view(M, ld)[:, :n_vocab]
-        linear(x, w, bias, out=lg, n=n_vocab, prec=prec)
-        _check(load().dsc_argmax_rows(lg.data_ptr(), lg.stride(0), ids_out.data_ptr(),
+        # `predictions` requested: tensor-core projection into the caller's logits rows, then the row argmax kernel
+        linear(x, w, bias, out=logits, n=n_vocab, prec=prec)
+        _check(load().dsc_argmax_rows(logits.data_ptr(), logits.stride(0), ids_out.data_ptr(),
                                       ids_out.stride(0) if M > 1 else 1, M, n_vocab, _stream()), "dsc_argmax_rows")
         return ids_out
     _check(load().dsc_vocab_argmax(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), bias.data_ptr(),

@@ -178,6 +178,17 @@ int dsc_vocab_argmax(const float* x, int64_t ldx, const float* w, int64_t ldw, c
                      int M, int N, int prec, void* stream);
 int64_t dsc_vocab_argmax_workspace(int M, int N);   /* floats */
 
+/* K12+K13 on tcgen05: same result as dsc_vocab_argmax with the projection on the tensor cores (prec 1 = bf16x3,
+ * 2 = bf16) and the logits never leaving the SM: every CTA keeps a running (max, first index) per row over its
+ * range of 64-column vocabulary tiles; the last CTA of a 256-row block folds the per-range partials in ascending
+ * column order (first maximum wins, like tf.argmax).  packed_w = dsc_pack_weight of the [128, N] kernel.
+ * workspace: dsc_vocab_argmax_tc_workspace(M, N) BYTES, 16-byte aligned, zero-filled by the caller before the FIRST
+ * call (its arrival counters reset themselves, so it can be reused by later calls of the same shape). */
+int64_t dsc_vocab_argmax_tc_workspace(int M, int N);   /* bytes */
+int dsc_vocab_argmax_tc(const float* x, int64_t ldx, const void* packed_w, const float* bias,
+                        int32_t* ids, int64_t ids_stride, void* workspace, int64_t workspace_bytes,
+                        int M, int N, int prec, void* stream);
+
 /* K13 standalone: row-wise argmax of materialised logits. */
 int dsc_argmax_rows(const float* logits, int64_t ld, int32_t* ids, int64_t ids_stride, int M, int N, void* stream);
 

@@ -272,6 +272,46 @@ def test_vocab_argmax_and_ce_rows(L, dev):
     assert L.argmax_rows(tie).tolist() == [17, 999, 0]
 
 
+@pytest.mark.parametrize("M", [96, 700])
+@pytest.mark.parametrize("prec", [1, 2])
+def test_vocab_argmax_tensor_core_fused(L, dev, M, prec):
+    """dsc_vocab_argmax_tc: ids equal the fp64 argmax wherever the margin is not a numerical tie (bf16x3), exact
+    ties resolve to the smallest index across tiles and across CTAs, untouched id columns stay untouched."""
+    P = _cases.params("Transeiver_Star")
+    g = torch.Generator().manual_seed(16)
+    x = torch.randn(M, 128, generator=g)
+    w, b = P["semantic_decoder/final_layer/kernel"].clone(), P["semantic_decoder/final_layer/bias"].clone()
+    V = w.shape[1]
+    # rows 0..2: three identical winning columns placed in different 64-column tiles / CTA ranges
+    for r, cols in enumerate(([5, 900, 20000], [22233, 22200, 64], [12345, 12346, 12347])):
+        for c in cols:
+            w[:, c] = x[r] / x[r].norm() * 3.0
+            b[c] = 0.25
+    logits = x.double() @ w.double() + b.double()
+    wd = torch.zeros(128, (V + 127) // 128 * 128, device=dev)
+    wd[:, :V] = w.to(dev)
+    ids = torch.full((M, 3), -7, dtype=torch.int32, device=dev)
+    for _ in range(2):                                  # second call reuses the self-resetting workspace
+        ids[:, 1] = -7
+        L.vocab_argmax(x.to(dev), wd, b.to(dev), V, ids[:, 1], prec=prec)
+    got = ids[:, 1].cpu().long()
+    assert got[:3].tolist() == [5, 64, 12345]
+    # the planted duplicate columns tie exactly (same operands, same arithmetic) for every row, so most rows test the
+    # first-index rule; a row is "clear" when the gap to the best non-tied value is not a numerical tie
+    mx = logits.max(-1).values
+    second = logits.masked_fill(logits == mx[:, None], -float("inf")).max(-1).values
+    clear = (mx - second) > (1e-5 if prec == 1 else 5e-2)
+    assert clear.float().mean() > (0.95 if prec == 1 else 0.3)
+    want = torch.from_numpy(np.argmax(logits.numpy(), axis=-1))          # first occurrence
+    assert torch.equal(got[clear], want[clear])
+    assert bool((ids[:, 0] == -7).all()) and bool((ids[:, 2] == -7).all())
+    if prec == 1:                                       # same ids as the unfused tensor-core path (logits materialised)
+        lg = torch.empty(M, V, device=dev)
+        ids2 = torch.zeros(M, dtype=torch.int32, device=dev)
+        L.vocab_argmax(x.to(dev), wd, b.to(dev), V, ids2, logits=lg, prec=1)
+        assert torch.equal(ids2.cpu().long(), got)
+
+
 def test_bleu_counts_bit_exact_on_real_sentences(L, dev):
     fix = json.load(open(os.path.join(_cases.GOLDEN_DIR, "europarl_sample.json")))
     from test_bleu_oracle import corrupt, pad
