@@ -50,6 +50,22 @@ _SIGNATURES = {
     "dsc_masked_ce_rows": (C.c_int, [vp, i64, vp, vp, i32, i32, vp]),
     "dsc_bleu_counts": (C.c_int, [vp, i32, vp, i32, vp, i32, vp]),
     "dsc_fgm_normalize": (C.c_int, [vp, vp, f32, i32, i32, i32, vp]),
+    # backward kernels (K17)
+    "dsc_gemm": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, i32, i32, vp]),
+    "dsc_bias_act_backward": (C.c_int, [vp, i64, vp, i64, i32, vp, i64, vp, i32, i32, vp]),
+    "dsc_add_layernorm_backward": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, vp]),
+    "dsc_mha_attention_backward": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,
+                                             vp, i64, i64, vp, vp, i64, i64, i32, i32, i32, vp]),
+    "dsc_star_satellite_attn_backward": (C.c_int, [vp, vp, vp, vp, vp, i32, vp]),
+    "dsc_star_relay_attn_backward": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, i32, vp]),
+    "dsc_embed_backward": (C.c_int, [vp, i64, vp, i64, vp, i32, i32, i32, vp]),
+    "dsc_star_pack_backward": (C.c_int, [vp, vp, i32, vp]),
+    "dsc_masked_ce_backward": (C.c_int, [vp, i64, vp, vp, vp, i64, i32, i32, vp]),
+    "dsc_unit_dot": (C.c_int, [vp, vp, vp, i32, i64, vp]),
+    "dsc_power_normalize_backward": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, i64, vp]),
+    "dsc_channel_backward": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, i32, i64, vp]),
+    "dsc_dropout": (C.c_int, [vp, vp, f32, u64, u64, i64, vp]),
+    "dsc_adam_step": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, f32, f32, i32, f32, f32, i64, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -151,23 +167,35 @@ def embed(ids: torch.Tensor, table: torch.Tensor, pos_table: torch.Tensor, pos0:
 
 
 _PACK_CACHE = {}
+# bumped by anything that rewrites parameters through raw pointers (the Adam kernel): torch's own _version counter
+# does not see those writes, and the packed / padded weight caches key on both
+WEIGHT_EPOCH = 0
+
+
+def weights_changed() -> None:
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
 
 
 def packed_weight(w: torch.Tensor, n: int) -> torch.Tensor:
-    """bf16 hi/lo UMMA image of a Keras-layout weight (cached per storage + version)."""
-    key = (w.data_ptr(), w._version, tuple(w.shape), w.stride(0), n, w.device.index)
+    """bf16 hi/lo UMMA image of a Keras-layout weight, cached per storage and re-packed in place when the weight
+    has been modified (torch version counter or WEIGHT_EPOCH)."""
+    key = (w.data_ptr(), tuple(w.shape), w.stride(0), n, w.device.index)
+    stamp = (w._version, WEIGHT_EPOCH)
     hit = _PACK_CACHE.get(key)
-    if hit is None:
+    if hit is None or hit[0] != stamp:
         K = w.shape[0]
-        nbytes = load().dsc_packed_weight_bytes(K, n)
-        blob = torch.empty((nbytes,), device=w.device, dtype=torch.uint8)
+        if hit is None:
+            if len(_PACK_CACHE) > 512:
+                _PACK_CACHE.clear()
+            blob = torch.empty((load().dsc_packed_weight_bytes(K, n),), device=w.device, dtype=torch.uint8)
+        else:
+            blob = hit[1]
         _check(load().dsc_pack_weight(_f32(w).data_ptr(), w.stride(0), K, n, blob.data_ptr(), _stream()),
                "dsc_pack_weight")
-        if len(_PACK_CACHE) > 256:
-            _PACK_CACHE.clear()
-        hit = (blob, w)          # keep the source alive so its data_ptr cannot be recycled under the key
+        hit = (stamp, blob, w)   # keep the source alive so its data_ptr cannot be recycled under the key
         _PACK_CACHE[key] = hit
-    return hit[0]
+    return hit[1]
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0,

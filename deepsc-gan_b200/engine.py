@@ -14,6 +14,7 @@ restructured for throughput without changing a result:
 """
 from __future__ import annotations
 
+import math
 from typing import List, Optional, Sequence
 
 import torch
@@ -28,18 +29,35 @@ START_IDX = 1
 def transmit(net, inp: torch.Tensor, n_units: int, n_std: torch.Tensor, *, channel: str = "AWGN",
              noise: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
              h: Optional[torch.Tensor] = None, p: Optional[torch.Tensor] = None,
-             p_scale: Optional[torch.Tensor] = None, detector: int = 0):
-    """inp [S,31] int32 -> (raw symbols [S,31,16], received symbols [S,31,16]).  Encoder + channel
-    encoder + fused power-norm/channel.  n_std [n_units]; h [n_units,2] for fading; p/p_scale for AWGN."""
+             p_scale: Optional[torch.Tensor] = None, detector: int = 0, want_x_norm: bool = False,
+             attack: Optional[str] = None, PNR_dB: float = 0.0):
+    """inp [S,31] int32 -> (symbols [S,31,16], received symbols [S,31,16]).  Encoder + channel encoder + fused
+    power-norm/channel.  n_std [n_units]; h [n_units,2] for fading; p/p_scale for AWGN.  The first item is the raw
+    channel-encoder output unless ``want_x_norm`` (then the power-normalised symbols, Channel_Encoder's return value).
+
+    ``attack="generator"`` (config 4, ``Transeiver_GAN``): the perturbation is G(x) of models/gan.py:4-16 normalised to unit
+    Frobenius norm per unit and enters Channels.awgn as n_std*sqrt(PNR)*sqrt(size)*p
+    (models/transceiver.py:29-32), so that PSR_dB = PNR_dB - SNR_dB."""
     enc_mask = M.create_padding_mask(inp)
     sem = net.semantic_encoder.call(inp, False, enc_mask)
     u = net.channel_encoder.raw(sem).contiguous()
     sumsq = _lib.unit_sumsq(u, n_units)
     if channel != "AWGN" and h is None:
         raise ValueError("fading channels need the per-unit coefficients h [n_units, 2]")
-    y, _ = _lib.channel(u, n_units, n_std, x_sumsq=sumsq, x_factor=1.0, noise=noise, seed=seed, offset=offset,
-                        p=p, p_scale=p_scale, h=h if channel != "AWGN" else None, detector=detector)
-    return u, y
+    hh = h if channel != "AWGN" else None
+    if attack == "generator":
+        if channel != "AWGN":
+            raise ValueError("the perturbation is ignored by the fading channel (models/transceiver.py:35-83)")
+        x = _lib.power_normalize(u, n_units, 1.0, sumsq=sumsq)
+        g = net.generator.raw(x).contiguous()
+        elems = g.numel() // n_units
+        ps = n_std * (math.sqrt(10 ** (PNR_dB / 10)) * math.sqrt(float(elems)))
+        y, _ = _lib.channel(x, n_units, n_std, noise=noise, seed=seed, offset=offset, p=g,
+                            p_sumsq=_lib.unit_sumsq(g, n_units), p_factor=float(elems), p_scale=ps.contiguous())
+        return x, y
+    y, xn = _lib.channel(u, n_units, n_std, x_sumsq=sumsq, x_factor=1.0, noise=noise, seed=seed, offset=offset,
+                         p=p, p_scale=p_scale, h=hh, detector=detector, want_x_norm=want_x_norm)
+    return (xn if want_x_norm else u), y
 
 
 class _StarLayerState:
@@ -159,11 +177,12 @@ def make_decoder(net, n_sent: int, max_length: int = 30):
 
 def greedy_units(net, inp: torch.Tensor, n_units: int, n_std: torch.Tensor, *, channel: str = "AWGN",
                  noise=None, seed: int = 0, offset: int = 0, h=None, p=None, p_scale=None, detector: int = 0,
-                 max_length: int = 30, start_idx: int = START_IDX, decoder=None) -> torch.Tensor:
+                 max_length: int = 30, start_idx: int = START_IDX, decoder=None, attack: Optional[str] = None,
+                 PNR_dB: float = 0.0) -> torch.Tensor:
     """Transmit + greedy decode for ``n_units`` units stacked along the batch axis.  Returns ids [S, 31]."""
     inp = inp.to(torch.int32).contiguous()
     _, y = transmit(net, inp, n_units, n_std, channel=channel, noise=noise, seed=seed, offset=offset, h=h, p=p,
-                    p_scale=p_scale, detector=detector)
+                    p_scale=p_scale, detector=detector, attack=attack, PNR_dB=PNR_dB)
     if decoder is None:
         decoder = make_decoder(net, inp.shape[0], max_length)
     if isinstance(decoder, StarGreedyDecoder):

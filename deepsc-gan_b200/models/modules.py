@@ -12,8 +12,11 @@ identity (modules.py:389-401), star attention is cyclic and unmasked (:289-299),
 ``layernorm1`` twice (:310,:314), the 4-layer star layers drive the relay with the satellite weights
 (:175,:243), the star decoders emit 31 (memory-length) positions (:376).
 
-Only inference is implemented (``training=True`` with a non-zero dropout raises): the backward
-kernels of SURVEY.md K17 are not part of this revision.
+Two execution modes share these classes.  The default (inference) mode reuses workspaces, writes in place
+and takes the fused tcgen05 kernels.  Inside ``with differentiable():`` every op goes through the
+``torch.autograd.Function`` wrappers of ``..autograd`` (forward and backward both libdeepsc_b200.so kernels,
+SURVEY.md K17), out of place, so that ``utlis`` can take d(loss)/d(symbols) and parameter gradients;
+``training=True`` additionally applies dropout at the reference's sites (Philox mask kernel).
 """
 from __future__ import annotations
 
@@ -25,6 +28,7 @@ import torch
 from torch import nn
 
 from .. import _lib
+from .. import autograd as AG
 
 D_MODEL = 128
 PREC = 0   # precision knob passed to dsc_linear: 0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16
@@ -35,6 +39,40 @@ def set_precision(prec: int) -> None:
     global PREC
     assert prec in (0, 1, 2)
     PREC = prec
+
+
+_DIFF = False
+_DROPOUT = {"seed": 0x5EED, "calls": 0}
+
+
+class differentiable:
+    """Context manager: route every op through the autograd Functions (out of place, unfused star cycles)."""
+
+    def __enter__(self):
+        global _DIFF
+        self._prev, _DIFF = _DIFF, True
+        return self
+
+    def __exit__(self, *exc):
+        global _DIFF
+        _DIFF = self._prev
+        return False
+
+
+def is_differentiable() -> bool:
+    return _DIFF
+
+
+def set_dropout_seed(seed: int) -> None:
+    _DROPOUT["seed"], _DROPOUT["calls"] = int(seed), 0
+
+
+def _dropout(x: torch.Tensor, rate: float, training) -> torch.Tensor:
+    """tf.keras.layers.Dropout(rate)(x, training=training)."""
+    if not training or rate <= 0:
+        return x
+    _DROPOUT["calls"] += 1
+    return AG.Dropout.apply(x, float(rate), _DROPOUT["seed"], _DROPOUT["calls"])
 
 
 def postional_encoder(position: int, d_model: int) -> torch.Tensor:
@@ -64,7 +102,7 @@ class Dense(nn.Module):
         k = self.kernel
         if k.shape[1] % 4 == 0:
             return k.detach()
-        key = (k._version, k.data_ptr(), k.device)
+        key = (k._version, _lib.WEIGHT_EPOCH, k.data_ptr(), k.device)
         if self._packed is None or self._packed[0] != key:
             n_pad = (k.shape[1] + 127) // 128 * 128
             buf = torch.zeros((k.shape[0], n_pad), device=k.device, dtype=torch.float32)
@@ -73,6 +111,8 @@ class Dense(nn.Module):
         return self._packed[1]
 
     def forward(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if _DIFF:
+            return AG.linear(x, self.kernel, self.bias, self.act, PREC, wfwd=self.padded_kernel())
         lead = x.shape[:-1]
         x2 = x.reshape(-1, x.shape[-1])
         y = _lib.linear(x2, self.padded_kernel(), None if self.bias is None else self.bias.detach(), self.act,
@@ -104,16 +144,33 @@ def _as_ids(x: torch.Tensor) -> torch.Tensor:
 
 
 def _check_eval(training, rate: float) -> None:
-    if training and rate > 0:
-        raise NotImplementedError("training=True (dropout + backward) is not implemented in this revision; "
-                                  "see DESIGN.md 'out of scope / next'")
+    if training and rate > 0 and not _DIFF:
+        raise RuntimeError("training=True with dropout runs in the differentiable mode only: wrap the call in "
+                           "`with models.modules.differentiable():` (utlis.trainer / utlis.gan_train do)")
 
 
 def _add_ln(x: torch.Tensor, res: Optional[torch.Tensor], ln_a: LayerNormalization,
             ln_b: Optional[LayerNormalization] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if _DIFF:
+        return AG.add_layernorm(x, res, ln_a, ln_b)
     return _lib.add_layernorm(x, res, ln_a.gamma.detach(), ln_a.beta.detach(),
                               None if ln_b is None else ln_b.gamma.detach(),
                               None if ln_b is None else ln_b.beta.detach(), out=out)
+
+
+def _res_ln(attn: torch.Tensor, res: torch.Tensor, ln: LayerNormalization, training, rate: float) -> torch.Tensor:
+    """LN(res + dropout(attn)): the attention sub-block of every layer (e.g. models/modules.py:424-425)."""
+    return _add_ln(_dropout(attn, rate, training), res, ln)
+
+
+def _res_ln2(attn: torch.Tensor, res: torch.Tensor, ln_a: LayerNormalization, ln_b: LayerNormalization, training,
+             rate: float) -> torch.Tensor:
+    """o1 = LN_a(res + dropout(attn)); LN_b(o1 + dropout(ffn(o1))) with the identity feed-forward (:424-429 and the
+    same pattern in every layer).  Without dropout this is the fused LN_b(2 * LN_a(.)) kernel."""
+    if training and rate > 0:
+        o1 = _add_ln(_dropout(attn, rate, training), res, ln_a)
+        return _add_ln(_dropout(o1, rate, training), o1, ln_b)
+    return _add_ln(attn, res, ln_a, ln_b)
 
 
 # --------------------------------------------------------------------------- multi-head attention
@@ -134,7 +191,7 @@ class sublayer1(nn.Module):
         """Concatenated projection weights: 'qkv' [128,384], 'kv' [128,256]."""
         ws = {"qkv": (self.wq, self.wk, self.wv), "kv": (self.wk, self.wv),
               "qkv_grouped": (self.wq, self.wk, self.wv)}[which]
-        key = tuple((w.kernel._version, w.kernel.data_ptr()) for w in ws)
+        key = (_lib.WEIGHT_EPOCH,) + tuple((w.kernel._version, w.kernel.data_ptr()) for w in ws)
         hit = self._cache.get(which)
         if hit is None or hit[0] != key:
             if which == "qkv_grouped":      # head pairs g: [wq[:,32g:32g+32] | wk[...] | wv[...]] (dsc_star_sat_tc)
@@ -146,10 +203,21 @@ class sublayer1(nn.Module):
             self._cache[which] = hit
         return hit[1]
 
+    def project(self, x2: torch.Tensor, which: str) -> torch.Tensor:
+        """x2 [rows,128] @ concatenated projection weights ('qkv' -> [rows,384], 'kv' -> [rows,256]), in either mode.
+        In the differentiable mode the weight operand is the (differentiable) concatenation of the kernels, whose
+        backward is the slicing; the forward kernel still reads the cached packed copy."""
+        if _DIFF:
+            ws = (self.wq, self.wk, self.wv) if which == "qkv" else (self.wk, self.wv)
+            return AG.linear(x2, torch.cat([w.kernel for w in ws], dim=1), None, 0, PREC, wfwd=self._packed(which))
+        return _lib.linear(x2, self._packed(which), None, prec=PREC)
+
     def attend(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask=None, key_ids=None,
                causal: bool = False, q_off: int = 0) -> torch.Tensor:
         """Projected q [n,lq,128] / k,v [n,lk,128] views -> dense(softmax(qk^T/4 + mask*-1e9) v)."""
         n, lq, _ = q.shape
+        if _DIFF:
+            return self.dense(AG.MhaAttention.apply(q, k, v, mask, key_ids, causal, q_off))
         o = torch.empty((n, lq, D_MODEL), device=q.device, dtype=torch.float32)
         _lib.mha_attention(q, k, v, o, mask=mask, key_ids=key_ids, causal=causal, q_off=q_off)
         return self.dense(o)
@@ -158,12 +226,12 @@ class sublayer1(nn.Module):
         n, lq, _ = q.shape
         lk = k.shape[1]
         if q is k and k is v:
-            qkv = _lib.linear(q.reshape(-1, D_MODEL), self._packed("qkv"), None, prec=PREC).view(n, lq, 384)
+            qkv = self.project(q.reshape(-1, D_MODEL), "qkv").view(n, lq, 384)
             Q, K, V = qkv[..., 0:128], qkv[..., 128:256], qkv[..., 256:384]
         else:
             Q = self.wq(q)
             if k is v:
-                kv = _lib.linear(k.reshape(-1, D_MODEL), self._packed("kv"), None, prec=PREC).view(n, lk, 256)
+                kv = self.project(k.reshape(-1, D_MODEL), "kv").view(n, lk, 256)
                 K, V = kv[..., 0:128], kv[..., 128:256]
             else:
                 K, V = self.wk(k), self.wv(v)
@@ -232,6 +300,8 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
     relay weights (decoder only), of which the first n2 rows are attended; ``kv2i`` is the same cache
     already in the interleaved layout of the tcgen05 kernels."""
     S = e_tile.shape[0]
+    if _DIFF:
+        return _star_cycles_diff(e_tile, sat, relay, cycle_num, kv2, n2)
     if ws is None:
         ws = StarWorkspace(S, e_tile.device)
     if not kv_e_ready:
@@ -272,10 +342,36 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
     return ws.x
 
 
-def _target_branch(layer, tar: torch.Tensor, look_ahead_mask) -> Tuple[torch.Tensor, torch.Tensor]:
-    """h2 = LN1(tar + multi_tar(tar,tar,tar,mask)) and its relay-weight k|v (modules.py:352-354)."""
-    h2 = _add_ln(layer.multi_tar(tar, tar, tar, look_ahead_mask), tar, layer.layernorm1)
-    return h2
+def _star_cycles_diff(e_tile: torch.Tensor, sat: "sublayer1", relay: "sublayer1", cycle_num: int,
+                      kv2: Optional[torch.Tensor], n2: int) -> torch.Tensor:
+    """The same cycle loop, out of place on the autograd Functions (one kernel per op, fp32 or tcgen05 Dense)."""
+    S = e_tile.shape[0]
+    x = e_tile
+    kv_e = sat.project(e_tile.reshape(S * 32, 128), "kv")
+    for _ in range(cycle_num):
+        qkv = sat.project(x.reshape(S * 32, 128), "qkv")
+        att = AG.StarSatelliteAttn.apply(qkv, kv_e)
+        h = AG.linear(att, sat.dense.kernel, sat.dense.bias, 1, PREC, wfwd=sat.dense.kernel.detach()).view(S, 32, 128)
+        x = torch.cat([h[:, :31], x[:, 31:32]], dim=1)                   # the relay row keeps s
+        qkv_r = relay.project(x.reshape(S * 32, 128), "qkv")
+        att_r = AG.StarRelayAttn.apply(qkv_r, kv2, n2)
+        s = AG.linear(att_r, relay.dense.kernel, relay.dense.bias, 1, PREC, wfwd=relay.dense.kernel.detach())
+        x = torch.cat([x[:, :31], s[:, None, :]], dim=1)
+    return x
+
+
+def _star_pack(e: torch.Tensor) -> torch.Tensor:
+    return AG.StarPack.apply(e) if _DIFF else _lib.star_pack(e.contiguous())
+
+
+def _kv_of(x2: torch.Tensor, att: "sublayer1") -> torch.Tensor:
+    """k|v projection [rows, 256] of rows x2 under the weights of ``att``."""
+    return att.project(x2, "kv")
+
+
+def _target_branch(layer, tar: torch.Tensor, look_ahead_mask, training=False) -> torch.Tensor:
+    """h2 = LN1(tar + dropout1(multi_tar(tar,tar,tar,mask))) (modules.py:219-221, 352-354)."""
+    return _res_ln(layer.multi_tar(tar, tar, tar, look_ahead_mask), tar, layer.layernorm1, training, layer.drop_pro)
 
 
 class _StarBase(nn.Module):
@@ -297,9 +393,9 @@ class StarTransformerEncoderLayer(_StarBase):
 
     def forward(self, e, training, forward=True, mask=None):
         _check_eval(training, self.drop_pro)
-        tile = _lib.star_pack(e.contiguous())
+        tile = _star_pack(e)
         x = star_cycles(tile, self.multi_att_satellite, self.multi_att_satellite, self.cycle_num)
-        out = _add_ln(x[:, :31], tile[:, :31], self.layernorm1, self.layernorm2)
+        out = _res_ln2(x[:, :31], tile[:, :31], self.layernorm1, self.layernorm2, training, self.drop_pro)
         return out, x[:, 31, :].clone()
 
     call = forward
@@ -319,12 +415,12 @@ class StarTransformerDecoderLayer(_StarBase):
 
     def forward(self, tar, e, look_ahead_mask, training, forward=True, mask=None):
         _check_eval(training, self.drop_pro)
-        h2 = _target_branch(self, tar, look_ahead_mask)
+        h2 = _target_branch(self, tar, look_ahead_mask, training)
         b, lt, _ = h2.shape
-        kv2 = _lib.linear(h2.view(b * lt, 128), self.multi_att_satellite._packed("kv"), None, prec=PREC).view(b, lt, 256)
-        tile = _lib.star_pack(e.contiguous())
+        kv2 = _kv_of(h2.reshape(b * lt, 128), self.multi_att_satellite).view(b, lt, 256)
+        tile = _star_pack(e)
         x = star_cycles(tile, self.multi_att_satellite, self.multi_att_satellite, self.cycle_num, kv2, lt)
-        out = _add_ln(x[:, :31], tile[:, :31], self.layernorm1, self.layernorm2)
+        out = _res_ln2(x[:, :31], tile[:, :31], self.layernorm1, self.layernorm2, training, self.drop_pro)
         return out, x[:, 31, :].clone()
 
     call = forward
@@ -345,9 +441,9 @@ class STE(_StarBase):
 
     def forward(self, e, training, forward=True, mask=None):
         _check_eval(training, self.drop_pro)
-        tile = _lib.star_pack(e.contiguous())
+        tile = _star_pack(e)
         x = star_cycles(tile, self.multi_att_satellite, self.multi_att_relay, self.cycle_num)
-        out = _add_ln(x[:, :31], tile[:, :31], self.layernorm1, self.layernorm1)
+        out = _res_ln2(x[:, :31], tile[:, :31], self.layernorm1, self.layernorm1, training, self.drop_pro)
         return out, x[:, 31, :].clone()
 
     call = forward
@@ -369,12 +465,12 @@ class STD(_StarBase):
 
     def forward(self, tar, e, look_ahead_mask, training, forward=True, mask=None):
         _check_eval(training, self.drop_pro)
-        h2 = _target_branch(self, tar, look_ahead_mask)
+        h2 = _target_branch(self, tar, look_ahead_mask, training)
         b, lt, _ = h2.shape
-        kv2 = _lib.linear(h2.view(b * lt, 128), self.multi_att_relay._packed("kv"), None, prec=PREC).view(b, lt, 256)
-        tile = _lib.star_pack(e.contiguous())
+        kv2 = _kv_of(h2.reshape(b * lt, 128), self.multi_att_relay).view(b, lt, 256)
+        tile = _star_pack(e)
         x = star_cycles(tile, self.multi_att_satellite, self.multi_att_relay, self.cycle_num, kv2, lt)
-        out = _add_ln(x[:, :31], tile[:, :31], self.layernorm2, self.layernorm3)
+        out = _res_ln2(x[:, :31], tile[:, :31], self.layernorm2, self.layernorm3, training, self.drop_pro)
         return out, x[:, 31, :].clone()
 
     call = forward
@@ -394,7 +490,7 @@ class EncoderLayer(nn.Module):
 
     def forward(self, x, training, mask):
         _check_eval(training, self.drop_pro)
-        return _add_ln(self.sl1(x, x, x, mask), x, self.layernorm1, self.layernorm2)
+        return _res_ln2(self.sl1(x, x, x, mask), x, self.layernorm1, self.layernorm2, training, self.drop_pro)
 
     call = forward
 
@@ -414,17 +510,22 @@ class DecoderLayer(nn.Module):
 
     def forward(self, x, enc_output, training, look_ahead_mask, padding_mask):
         _check_eval(training, self.drop_pro)
-        o1 = _add_ln(self.sl11(x, x, x, look_ahead_mask), x, self.layernorm1)
-        return _add_ln(self.sl12(o1, enc_output, enc_output, padding_mask), o1, self.layernorm2, self.layernorm3)
+        o1 = _res_ln(self.sl11(x, x, x, look_ahead_mask), x, self.layernorm1, training, self.drop_pro)
+        return _res_ln2(self.sl12(o1, enc_output, enc_output, padding_mask), o1, self.layernorm2, self.layernorm3,
+                        training, self.drop_pro)
 
     call = forward
 
 
 # --------------------------------------------------------------------------- encoders / decoders
 class _Codec(nn.Module):
-    def _embed(self, ids: torch.Tensor, pos0: int = 0) -> torch.Tensor:
+    def _embed(self, ids: torch.Tensor, pos0: int = 0, training=False) -> torch.Tensor:
+        """Embedding * sqrt(d_model) + positional rows, then the codec's input Dropout (e.g. :497-505)."""
         if self.pos_encoding.device != self.embedding.embeddings.device:
             self.pos_encoding = self.pos_encoding.to(self.embedding.embeddings.device)
+        if _DIFF:
+            x = AG.Embed.apply(_as_ids(ids), self.embedding.embeddings, self.pos_encoding[0], pos0)
+            return _dropout(x, self.dropout_pro, training)
         return _lib.embed(_as_ids(ids), self.embedding.embeddings.detach(), self.pos_encoding[0], pos0)
 
 
@@ -442,7 +543,7 @@ class Encoder(_Codec):
 
     def forward(self, x, training, mask):
         _check_eval(training, self.dropout_pro)
-        x = self._embed(x)
+        x = self._embed(x, training=training)
         for layer in self.encoder:
             x = layer(x, training, mask)
         return x
@@ -463,7 +564,7 @@ class Decoder(_Codec):
         self.final_layer = Dense(d_model, target_vocab_size)
 
     def hidden(self, x, enc_output, training, look_ahead_mask, padding_mask):
-        x = self._embed(x)
+        x = self._embed(x, training=training)
         for layer in self.dec_layers:
             x = layer(x, enc_output, training, look_ahead_mask, padding_mask)
         return x
@@ -490,7 +591,7 @@ class SEncoder(_Codec):
 
     def forward(self, x, training, mask):
         _check_eval(training, self.dropout_pro)
-        x = self._embed(x)
+        x = self._embed(x, training=training)
         for layer in self.encoder:
             x, _ = layer(x, training, True, mask)
         return x
@@ -512,7 +613,7 @@ class SDecoder(_Codec):
         self.final_layer = Dense(d_model, target_vocab_size)
 
     def hidden(self, tar, x, look_ahead_mask, training, mask):
-        tar = self._embed(tar)
+        tar = self._embed(tar, training=training)
         for layer in self.dec_layers:
             x, _ = layer(tar, x, look_ahead_mask, training, True, mask)
         return x
@@ -538,7 +639,7 @@ class SE(_Codec):
 
     def forward(self, x, training, mask):
         _check_eval(training, self.dropout_pro)
-        x, _ = self.encoder(self._embed(x), training, True, mask)
+        x, _ = self.encoder(self._embed(x, training=training), training, True, mask)
         return x
 
     call = forward
@@ -557,7 +658,7 @@ class SD(_Codec):
         self.final_layer = Dense(d_model, target_vocab_size)
 
     def hidden(self, tar, x, training, look_ahead_mask, mask):
-        x, _ = self.dec_layers(self._embed(tar), x, look_ahead_mask, training, True, mask)
+        x, _ = self.dec_layers(self._embed(tar, training=training), x, look_ahead_mask, training, True, mask)
         return x
 
     def forward(self, tar, x, training, look_ahead_mask, mask):
@@ -582,7 +683,7 @@ class CustomSchedule:
 def loss_function(real: torch.Tensor, pred: torch.Tensor) -> torch.Tensor:
     """models/modules.py:738-755: masked sparse CE (PAD only, the id-4/5 masks are overwritten
     :749-750), mean over all positions.  Row losses come from dsc_masked_ce_rows."""
-    rows = _lib.masked_ce_rows(pred, real)
+    rows = AG.MaskedCeRows.apply(pred, real) if _DIFF else _lib.masked_ce_rows(pred, real)
     return rows.sum() / rows.numel()
 
 

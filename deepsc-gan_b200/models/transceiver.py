@@ -16,6 +16,8 @@ import torch
 from torch import nn
 
 from .. import _lib
+from .. import autograd as AG
+from . import modules as _M
 from .gan import G
 from .modules import Decoder, Dense, Encoder, LayerNormalization, SD, SDecoder, SE, SEncoder, _add_ln
 
@@ -58,7 +60,10 @@ class Channels(nn.Module):
         scale = float(n_std) * math.sqrt(PNR) * (math.sqrt(float(x.numel())) if scale_by_sqrt_size else 1.0)
         ns = torch.full((1,), float(n_std), device=dev, dtype=torch.float32)
         ps = torch.full((1,), scale, device=dev, dtype=torch.float32)
-        y, _ = _lib.channel(x, 1, ns, noise=None if noise is None else noise.contiguous(), seed=self.seed,
+        noise = None if noise is None else noise.contiguous()
+        if _M.is_differentiable():
+            return AG.Channel.apply(x, p, 1, ns, noise, self.seed, self._next_offset(), ps, None, 0)
+        y, _ = _lib.channel(x, 1, ns, noise=noise, seed=self.seed,
                             offset=self._next_offset(), p=None if p is None else p.contiguous(), p_scale=ps)
         return y
 
@@ -77,9 +82,11 @@ class Channels(nn.Module):
             z = [float(h[0]), float(h[1])]
         hh = torch.tensor([mean + std * z[0], mean + std * z[1]], device=dev, dtype=torch.float32)
         ns = torch.full((1,), float(n_std), device=dev, dtype=torch.float32)
-        y, _ = _lib.channel(x, 1, ns, noise=None if noise is None else noise.contiguous(), seed=self.seed,
-                            offset=self._next_offset(), h=hh,
-                            detector=_DETECTORS[detector] if self.apply_detector else 0)
+        noise = None if noise is None else noise.contiguous()
+        det = _DETECTORS[detector] if self.apply_detector else 0
+        if _M.is_differentiable():
+            return AG.Channel.apply(x, None, 1, ns, noise, self.seed, self._next_offset(), None, hh, det)
+        y, _ = _lib.channel(x, 1, ns, noise=noise, seed=self.seed, offset=self._next_offset(), h=hh, detector=det)
         return y
 
 
@@ -96,6 +103,8 @@ class Channel_Encoder(nn.Module):
         return self.dense1(self.dense0(inputs))
 
     def forward(self, inputs):
+        if _M.is_differentiable():
+            return AG.PowerNormalize.apply(self.raw(inputs), 1, 1.0)
         return _lib.power_normalize(self.raw(inputs).contiguous(), 1, factor=1.0)
 
     call = forward
@@ -145,6 +154,14 @@ class _TranseiverBase(nn.Module):
     def num_parameters(self) -> int:
         return sum(p.numel() for p in self.parameters())
 
+    @staticmethod
+    def _tape(symbols: torch.Tensor) -> torch.Tensor:
+        """Inside ``differentiable()`` the channel symbols are always a tape variable, so that the evaluators can take
+        d(loss)/d(symbols) with frozen parameters (tf.GradientTape watches every intermediate, utlis/eval.py:197-213)."""
+        if _M.is_differentiable() and not symbols.requires_grad:
+            symbols.requires_grad_(True)
+        return symbols
+
 
 class Transeiver(_TranseiverBase):
     """models/transceiver.py:115-161: DeepSC baseline (4+4 post-LN layers with identity feed-forward)."""
@@ -162,7 +179,7 @@ class Transeiver(_TranseiverBase):
     def forward(self, inputs, tar_inp, p, PNR_dB, channel="AWGN", n_std=0.1, training=False, enc_padding_mask=None,
                 combined_mask=None, dec_padding_mask=None, *, noise=None, h=None):
         sema_enc_output = self.semantic_encoder.call(inputs, training, enc_padding_mask)
-        channel_enc_output = self.channel_encoder.call(sema_enc_output)
+        channel_enc_output = self._tape(self.channel_encoder.call(sema_enc_output))
         received = self.channel_layer(channel_enc_output, p, PNR_dB, n_std, channel, noise=noise, h=h)
         received_dec = self.channel_decoder.call(received)
         predictions = self.semantic_decoder.call(tar_inp, received_dec, training, combined_mask, dec_padding_mask)
@@ -189,7 +206,7 @@ class Transeiver_star(_TranseiverBase):
     def forward(self, inputs, tar_inp, p, PNR_dB, channel="AWGN", n_std=0.1, training=False, enc_padding_mask=None,
                 combined_mask=None, dec_padding_mask=None, *, noise=None, h=None):
         sema_enc_output = self.semantic_encoder.call(inputs, training, enc_padding_mask)
-        channel_enc_output = self.channel_encoder.call(sema_enc_output)
+        channel_enc_output = self._tape(self.channel_encoder.call(sema_enc_output))
         if channel == "AWGN":
             received = self.channel_layer.awgn(channel_enc_output, p, PNR_dB, n_std, noise=noise)
         elif channel == "Rayleigh":
@@ -219,7 +236,7 @@ class Transeiver_Star(_TranseiverBase):
     def forward(self, inputs, tar_inp, p, PNR_dB, channel="AWGN", n_std=0.1, training=False, enc_padding_mask=None,
                 combined_mask=None, dec_padding_mask=None, *, noise=None, h=None):
         sema_enc_output = self.semantic_encoder.call(inputs, training, enc_padding_mask)
-        channel_enc_output = self.channel_encoder.call(sema_enc_output)
+        channel_enc_output = self._tape(self.channel_encoder.call(sema_enc_output))
         received = self.channel_layer(channel_enc_output, p, PNR_dB, n_std, channel, noise=noise, h=h)
         received_dec = self.channel_decoder.call(received)
         predictions = self.semantic_decoder.call(tar_inp, received_dec, training, combined_mask, dec_padding_mask)
@@ -247,7 +264,7 @@ class Transeiver_GAN(_TranseiverBase):
                 enc_padding_mask=None, combined_mask=None, dec_padding_mask=None, traingan=False, *,
                 noise=None, h=None, noise_r=None, h_r=None):
         sema_enc_output = self.semantic_encoder.call(inputs, training, enc_padding_mask)
-        channel_enc_output = self.channel_encoder.call(sema_enc_output)
+        channel_enc_output = self._tape(self.channel_encoder.call(sema_enc_output))
         p = self.generator.call(channel_enc_output) if traingan else pertutation
         y_p = self.channel_layer(channel_enc_output, p, PNR_dB, n_std, channel, noise=noise, h=h)
         y_r = self.channel_layer(channel_enc_output, None, PNR_dB, n_std, channel, noise=noise_r, h=h_r)   # p = zeros :288

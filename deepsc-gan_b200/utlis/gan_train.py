@@ -1,0 +1,75 @@
+"""GAN training step: mirror of DeepSC-GAN/utlis/gan_train.py (gan_train_step :8-50, eval_step :53-83).
+
+One forward of ``Transeiver_GAN`` under the tape, then the reference's three optimizer applications:
+  A (:24-29)  loss   = CE(clean branch)                          on every variable except the generator ``g``;
+  B (:35-37)  g_loss = 10 - CE(perturbed branch)                  on the generator (trainable_variables[104:108]);
+  C (:39-44)  d_loss = l*CE(clean) + (1-l)*CE(perturbed)          on the receiver (channel decoder + semantic decoder;
+              'g', 'encoder', 'channel_encoder' frozen - intent per SURVEY.md App. B Q14).
+All three gradients are taken at the pre-update weights (one persistent tape), and all three losses are linear in
+CE_r and CE_p, so two backward sweeps fill two flat gradient buffers (d CE_r, d CE_p); with a process group the two
+buffers are all-reduced together in ONE NCCL collective, and the lambda mix of step C is folded into the Adam kernel.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from .. import optim as O
+from ..models.modules import create_masks, differentiable, loss_function
+from .eval import fgm_perturbation
+from .trainer import make_optimizer  # noqa: F401  (re-export: the optimizer the missing driver builds)
+
+
+def _is_generator(name: str) -> bool:
+    return name.startswith("generator.")
+
+
+def _is_receiver(name: str) -> bool:
+    return name.startswith("channel_decoder.") or name.startswith("semantic_decoder.")
+
+
+def gan_train_step(inp, tar, p, net, optim_net, lenmda, channel='AWGN', n_std=0.1, training=False, traingan=False, *,
+                   noise=None, noise_r=None, h=None, h_r=None, p_draw=None):
+    """utlis/gan_train.py:8-50.  ``p`` is overwritten as in the reference (:13-14): a normal draw of std n_std
+    normalised to unit Frobenius norm (``p_draw`` = injected unit-normal tensor; used only when traingan=False).
+    The forward always runs with training=True and PNR_dB = 40 (:16-18).  Returns (loss, g_loss, d_loss)."""
+    tar_inp, tar_real = tar[:, :-1], tar[:, 1:]
+    masks = create_masks(inp, tar_inp)
+    enc_padding_mask, combined_mask, dec_padding_mask = masks
+    dev = inp.device
+    if p_draw is None:
+        p_draw = torch.randn((inp.shape[0], inp.shape[1], 16), device=dev, dtype=torch.float32)
+    p = _lib.power_normalize(p_draw.contiguous(), 1, factor=float(p_draw.numel()))   # p / ||p||_F (n_std cancels)
+    fp = optim_net.fp
+    assert fp.grad_bucket.shape[0] >= 2, "gan_train_step needs two flat gradient buffers (make_optimizer default)"
+    fp.grad_bucket.zero_()
+    not_g = fp.select(lambda n: not _is_generator(n))
+    with differentiable():
+        predictions_p, predictions_r, _, _ = net(inp, tar_inp, p, 40, channel=channel, n_std=n_std, training=True,
+                                                 enc_padding_mask=enc_padding_mask, combined_mask=combined_mask,
+                                                 dec_padding_mask=dec_padding_mask, traingan=traingan, noise=noise,
+                                                 noise_r=noise_r, h=h, h_r=h_r)
+        ce_r = loss_function(tar_real, predictions_r)
+        ce_p = loss_function(tar_real, predictions_p)
+        fp.point_grads(0)
+        ce_r.backward(inputs=not_g, retain_graph=True)                       # d CE_r / d (everything but g)
+        fp.point_grads(1)
+        wanted = fp.select(lambda n: _is_receiver(n) or (traingan and _is_generator(n)))
+        ce_p.backward(inputs=wanted)                                         # d CE_p / d (receiver, generator)
+    scale = O.all_reduce_mean_scale(fp.grad_bucket)
+    g_r, g_p = fp.grad_bucket[0], fp.grad_bucket[1]
+    optim_net.apply(fp.ranges(lambda n: not _is_generator(n)), g_r, scale)                      # step A
+    optim_net.apply(fp.ranges(_is_generator), g_p, -scale)                                      # step B: 10 - CE_p
+    optim_net.apply(fp.ranges(_is_receiver), g_r, scale * float(lenmda), g_p, scale * (1.0 - float(lenmda)))   # step C
+    loss = ce_r.detach()
+    return loss, 10 - ce_p.detach(), float(lenmda) * loss + (1 - float(lenmda)) * ce_p.detach()
+
+
+def eval_step(inp, tar, net, channel='AWGN', n_std=0.1, epsilon=1, *, noise=None, noise2=None, noise2_r=None, h=None):
+    """utlis/gan_train.py:53-83 (stale in the reference: it unpacks 3 of 4 outputs and omits PNR_dB; intent kept):
+    FGM direction from the clean branch w.r.t. y_r, second forward with it, loss on the perturbed branch.
+    Returns (loss, loss_p)."""
+    from .eval import eval_step_FGM
+    loss, loss_p, _, _ = eval_step_FGM(inp, tar, net, 0, channel=channel, n_std=n_std, epsilon=epsilon, noise=noise,
+                                       noise2=noise2, noise2_r=noise2_r, h=h)
+    return loss, loss_p

@@ -207,6 +207,84 @@ int dsc_bleu_counts(const int32_t* ref, int ref_len, const int32_t* hyp, int hyp
 int dsc_fgm_normalize(const float* g, float* p, float epsilon, int n_units, int samples_per_unit,
                       int elems_per_sample, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * K17: backward kernels.  The reference differentiates with tf.GradientTape (utlis/eval.py:25-33, 197-213;
+ * utlis/trainer.py:17-25, 37-62; utlis/gan_train.py:15-44); each entry point below is the gradient of one forward
+ * entry point above, fp32, recomputing softmax weights / LayerNorm statistics instead of storing them.
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* C[M,N] (+)= op(A)[M,K] @ op(B)[K,N], fp32.  trans_a: A is stored [K, M] (lda >= M); trans_b: B is stored [N, K].
+ * Dense backward: dx = dz @ W^T (trans_b = 1 on the Keras kernel), dW = x^T @ dz (trans_a = 1).  accumulate != 0 adds
+ * into C.  Large-K, small-output products are split over K with atomic accumulation. */
+int dsc_gemm(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b,
+             float* C, int64_t ldc, int M, int N, int K, int accumulate, void* stream);
+
+/* dz = dy * (y > 0) for act = 1 (relu; dz may alias dy), and dbias[c] = sum_r dz[r][c] (dbias NULL: skipped;
+ * act = 0: dz is not written, only dbias is produced).  y is the forward output of dsc_linear. */
+int dsc_bias_act_backward(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int act,
+                          float* dz, int64_t ld_dz, float* dbias, int M, int N, void* stream);
+
+/* Gradient of dsc_add_layernorm (same row addressing).  dv = d(x + res) (the gradient of both x and res);
+ * dgamma_x / dbeta_x [128] are ACCUMULATED (caller zero-fills); the _b pair is NULL for the single-LN form. */
+int dsc_add_layernorm_backward(const float* x, int64_t x_group_stride, const float* res, int64_t res_group_stride,
+                               const float* gamma_a, const float* beta_a, const float* gamma_b, const float* beta_b,
+                               const float* dout, int64_t dout_group_stride, float* dv, int64_t dv_group_stride,
+                               float* dgamma_a, float* dbeta_a, float* dgamma_b, float* dbeta_b,
+                               int n_rows, int group_rows, void* stream);
+
+/* Gradient of dsc_mha_attention: dq [n, lq, 128] (ld_dq, dq_batch_stride), dk / dv [n, lk, 128] (shared strides). */
+int dsc_mha_attention_backward(const float* q, int64_t ldq, int64_t q_batch_stride,
+                               const float* k, const float* v, int64_t ldkv, int64_t kv_batch_stride,
+                               const float* dout, int64_t ldo, int64_t o_batch_stride,
+                               const float* mask, int64_t mask_b_stride, int64_t mask_q_stride,
+                               const int32_t* key_ids, int64_t key_ids_stride, int causal, int q_off,
+                               float* dq, int64_t ld_dq, int64_t dq_batch_stride,
+                               float* dk, float* dv, int64_t ld_dkv, int64_t dkv_batch_stride,
+                               int n, int lq, int lk, void* stream);
+
+/* Gradient of dsc_star_satellite_attn: dqkv [n_sent*32, 384] and dkv_e [n_sent*32, 256], fully written. */
+int dsc_star_satellite_attn_backward(const float* qkv, const float* kv_e, const float* datt,
+                                     float* dqkv, float* dkv_e, int n_sent, void* stream);
+
+/* Gradient of dsc_star_relay_attn: dqkv_r [n_sent*32, 384] fully written; dkv2 [n_sent, kv2_rows, 256] fully written
+ * (rows >= n2 are zero).  kv2_rows <= 32. */
+int dsc_star_relay_attn_backward(const float* qkv_r, const float* kv2, int kv2_rows, int n2, const float* dout,
+                                 float* dqkv_r, float* dkv2, int n_sent, void* stream);
+
+/* Gradient of dsc_embed with respect to the table: dtable[ids] += sqrt(128) * dout (atomic; caller zero-fills). */
+int dsc_embed_backward(const int32_t* ids, int64_t ids_stride, const float* dout, int64_t ld_dout,
+                       float* dtable, int vocab, int n_sent, int len, void* stream);
+
+/* Gradient of dsc_star_pack: dsrc[i] = dtile[i] + dtile[31] / 31. */
+int dsc_star_pack_backward(const float* dtile, float* dsrc, int n_sent, void* stream);
+
+/* Gradient of dsc_masked_ce_rows: dlogits[r] = grad_rows[r] * (softmax(logits[r]) - onehot(target[r])) * (target[r] != 0). */
+int dsc_masked_ce_backward(const float* logits, int64_t ld, const int32_t* target, const float* grad_rows,
+                           float* dlogits, int64_t ld_d, int M, int N, void* stream);
+
+/* out[u] = sum over unit u of a * b (the reduction the power-norm gradient needs). */
+int dsc_unit_dot(const float* a, const float* b, float* out, int n_units, int64_t elems_per_unit, void* stream);
+
+/* Gradient of dsc_power_normalize: dx = r*dy - x * r^3 * (factor/n) * dot[u], r = (factor*sumsq[u]/n)^(-1/2),
+ * dot = dsc_unit_dot(x, dy). */
+int dsc_power_normalize_backward(const float* x, const float* sumsq, const float* dot, float factor,
+                                 const float* dy, float* dx, int n_units, int64_t elems_per_unit, void* stream);
+
+/* Gradient of dsc_channel with respect to its (already normalised) symbol input and perturbation input:
+ * AWGN dx = dy, dp = p_scale[u] * dy; fading dx = conj(h) * dy (after undoing the detector), dp = 0.  dx or dp may be NULL. */
+int dsc_channel_backward(const float* dy, const float* h, const float* n_std, int detector, const float* p_scale,
+                         float* dx, float* dp, int n_units, int64_t elems_per_unit, void* stream);
+
+/* tf.keras.layers.Dropout in training mode (models/modules.py:179-183, 220, 246-250, 424-428, 458-466, 505, 546):
+ * out = keep ? x / (1 - rate) : 0 with a Philox4x32-10 keep mask keyed by (seed, offset, element); calling it on dy
+ * with the same (seed, offset) is the backward pass.  n % 4 == 0. */
+int dsc_dropout(const float* x, float* out, float rate, uint64_t seed, uint64_t offset, int64_t n, void* stream);
+
+/* One tf.keras.optimizers.Adam update on a flat fp32 buffer: g = grad * grad_scale (+ grad2 * grad2_scale when
+ * grad2 != NULL, the lambda-mix of utlis/gan_train.py:22); m, v moments; step >= 1 is the optimizer's iteration count. */
+int dsc_adam_step(float* param, const float* grad, const float* grad2, float* m, float* v, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, float grad2_scale, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,5 +170,5 @@ def test_submodule_calls_used_by_eval(dev):
 def test_training_mode_raises(dev):
     args, net = build("Transeiver_Star", dev)
     inp = _cases.synthetic_unit(0).to(dev)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="differentiable"):      # dropout + backward live in the differentiable mode
         net.semantic_encoder.call(inp, True, None)
