@@ -36,6 +36,7 @@ _SIGNATURES = {
     "dsc_star_kv2_put": (C.c_int, [vp, vp, i32, i32, vp]),
     "dsc_star_mix_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "dsc_star_relay_update": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp]),
+    "dsc_star_cycles_tc": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "dsc_star_relay_attn": (C.c_int, [vp, vp, i32, i32, vp, i32, vp]),
     "dsc_mha_attention": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,
                                     i32, i32, i32, vp]),
@@ -97,7 +98,7 @@ STATS = {"launches": 0}
 # when set to a list, the wrappers named in PROFILE_OPS append (op, start_event, end_event, meta) for bench.py's
 # roofline accounting (CUDA events on the launching stream around the single kernel launch)
 PROFILE = None
-PROFILE_OPS = ("dsc_star_sat_tc",)
+PROFILE_OPS = ("dsc_star_sat_tc", "dsc_star_cycles_tc")
 
 
 class _timed:
@@ -303,6 +304,26 @@ def star_mix_tc(atti: torch.Tensor, xi: torch.Tensor, x_rowmajor: Optional[torch
                                   bias_o.data_ptr(), q_relay.data_ptr(), _ptr(kv2i), n2, att_relay.data_ptr(), n_sent,
                                   prec, _stream()), "dsc_star_mix_tc")
     return att_relay
+
+
+def star_cycles_tc(xi0: torch.Tensor, s0: torch.Tensor, q0: torch.Tensor, kvei: torch.Tensor, kv2i: Optional[torch.Tensor],
+                   n2: int, w_grouped: torch.Tensor, wo: torch.Tensor, wkv_relay: torch.Tensor, wo_relay: torch.Tensor,
+                   wq_relay: torch.Tensor, bias_o: torch.Tensor, bias_o_relay: torch.Tensor, x_rowmajor: torch.Tensor,
+                   n_sent: int, n_cycles: int, prec: int) -> torch.Tensor:
+    """All star cycles of a layer in one persistent launch (see include/deepsc_b200.h dsc_star_cycles_tc)."""
+    _need_cuda(xi0, s0, q0, kvei, kv2i, w_grouped, wo, wkv_relay, wo_relay, wq_relay, bias_o, bias_o_relay, x_rowmajor)
+    for t in (xi0, s0, q0, kvei, x_rowmajor, bias_o, bias_o_relay):
+        assert t.is_contiguous()
+    assert kv2i is None or (kv2i.is_contiguous() and kv2i.numel() == n_sent * 8192)
+    assert x_rowmajor.numel() == n_sent * 4096 and xi0.numel() >= n_sent * 4096 and kvei.numel() == n_sent * 8192
+    with _timed("dsc_star_cycles_tc", (n_sent, n_cycles, n2)):
+        _check(load().dsc_star_cycles_tc(xi0.data_ptr(), s0.data_ptr(), q0.data_ptr(), kvei.data_ptr(), _ptr(kv2i), n2,
+                                         packed_weight(w_grouped, 384).data_ptr(), packed_weight(wo, 128).data_ptr(),
+                                         packed_weight(wkv_relay, 256).data_ptr(), packed_weight(wo_relay, 128).data_ptr(),
+                                         packed_weight(wq_relay, 128).data_ptr(), bias_o.data_ptr(),
+                                         bias_o_relay.data_ptr(), x_rowmajor.data_ptr(), n_sent, n_cycles, prec, _stream()),
+               "dsc_star_cycles_tc")
+    return x_rowmajor
 
 
 def star_relay_update(att_r: torch.Tensor, wo: torch.Tensor, bo: torch.Tensor, wq: torch.Tensor, s_out: torch.Tensor,

@@ -1,0 +1,495 @@
+// All cycles of a star layer in ONE persistent launch (K2+K3+K4 of SURVEY.md 2.3, models/modules.py:283-306, 359-378).
+//
+// The per-cycle kernels of dsc_star_tc.cu stream the node states X, the attention output ATT and the relay vectors
+// through HBM twice per cycle.  Here a CTA keeps one tile (4 sentences = 128 rows = 128 TMEM lanes) on chip for all
+// cycles: X and ATT live in tensor memory as the bf16 hi/lo A operands of the next UMMA, the relay vectors s / q in
+// shared memory, and only the constant keys (e-keys KVEI, cached target keys KV2I) are re-read - from L2, since a
+// tile's 256 KB of keys are touched every cycle.  The five weight matrices (512 KB as bf16 hi/lo planes) do not fit
+// in shared memory, so a producer thread streams them per job through a shared-memory ring with cp.async.bulk.
+//
+// Jobs of one cycle (one elected thread issues the UMMAs, M = 128, fp32 accumulators in TMEM):
+//   J0..J3  QKV of head pair g = X @ [Wq|Wk|Wv]_sat[g]          N = 96  -> satellite attention over the 5 keys
+//                                                                          {h[i+1], h[i], h[i-1], e[i], s} -> ATT (TMEM)
+//   J4      O   = ATT @ Wo_sat                                   N = 128 -> X' = relu(O + b) (relay row keeps s) -> X (TMEM)
+//   J5, J6  K|V = X' @ [Wk|Wv]_relay                              N = 128 each -> relay attention over 32 (+n2) keys -> att_r
+//   J7      R1  = att_r @ Wo_relay                                N = 128 -> s' = relu(R1 + b) -> relay row of X patched
+//   J8      R2  = s' @ Wq_relay                                   N = 128 -> q' (the next cycle's relay query)
+// J7/J8 use only the relay lane of each sentence (lane 31 of a warp quarter); the other 124 rows of those two UMMAs
+// are don't-care.  Accumulators alternate between two 128-column TMEM buffers, so the UMMA of job j+1 overlaps the
+// epilogue of job j wherever the data dependence allows (all of J0..J3, J5/J6, and J0 of the next cycle under J8).
+//
+// Warps: 0-7 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, hh = warp >> 2 the column half),
+// 8 = UMMA issuer, 9 = weight producer.  Arithmetic as in dsc_star_tc.cu: prec 1 = bf16x3, 2 = bf16; fp32 softmax.
+#include "dsc_star_common.cuh"
+
+namespace dsc {
+
+using namespace tc;
+
+namespace sf {
+constexpr int kCompute = 8, kMmaWarp = 8, kProdWarp = 9, kThreads = 320;
+constexpr int STAGES = 3;
+constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
+constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
+constexpr int JOBS = 9;
+
+struct Bars {
+  uint64_t w_full[STAGES], w_free[STAGES];
+  uint64_t acc_full[2], acc_free[2];
+  uint64_t x_ready, t_ready;
+};
+struct Weights {
+  const uint8_t* qkv;    // grouped [Wq|Wk|Wv]_sat, 384 rows
+  const uint8_t* wo;     // Wo_sat, 128 rows
+  const uint8_t* wkv;    // [Wk|Wv]_relay, 256 rows
+  const uint8_t* wo_r;   // Wo_relay
+  const uint8_t* wq_r;   // Wq_relay
+};
+// chunk j of a cycle: source blob, rows per plane, first row, rows of the blob (n_pad)
+__device__ __forceinline__ void chunk_of(const Weights& w, int j, const uint8_t*& blob, uint32_t& rows, uint32_t& row0, uint32_t& n_pad) {
+  if (j < 4)       { blob = w.qkv;  rows = 96;  row0 = 96u * j; n_pad = 384; }
+  else if (j == 4) { blob = w.wo;   rows = 128; row0 = 0;       n_pad = 128; }
+  else if (j == 5) { blob = w.wkv;  rows = 128; row0 = 0;       n_pad = 256; }
+  else if (j == 6) { blob = w.wkv;  rows = 128; row0 = 128;     n_pad = 256; }
+  else if (j == 7) { blob = w.wo_r; rows = 128; row0 = 0;       n_pad = 128; }
+  else             { blob = w.wq_r; rows = 128; row0 = 0;       n_pad = 128; }
+}
+}  // namespace sf
+
+// 64 fp32 values in shared memory -> 32 hi + 32 lo packed bf16 words (plain loads: load_half_row uses ld.global.nc)
+__device__ __forceinline__ void split_half_row_smem(const float* p, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const float4 v = reinterpret_cast<const float4*>(p)[q];
+    split2(v.x, v.y, hi[2 * q], lo[2 * q]);
+    split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
+  }
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(sf::kThreads, 1)
+star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, const float* __restrict__ Q0,
+                  const float* __restrict__ KVEI, const float* __restrict__ KV2I, int n2, sf::Weights W,
+                  const float* __restrict__ bias_o, const float* __restrict__ bias_r,
+                  float* __restrict__ Xrow, int n_tiles, int n_cycles) {
+  using namespace sf;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) sf::Bars bars;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_cur[4][128];      // relay node of the 4 sentences of the tile
+  __shared__ __align__(16) float q_cur[4][128];      // its query under the relay weights
+  __shared__ __align__(16) float attr[8][64];        // per compute warp: relay attention output (its column half)
+  constexpr int parts = (NPASS == 3) ? 2 : 1;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_free[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kCompute * 32); }
+    mbar_init(&bars.x_ready, kCompute * 32);
+    mbar_init(&bars.t_ready, kCompute * 32);
+    fence_barrier_init();
+  }
+  if (warp == sf::kMmaWarp) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == kProdWarp) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      uint32_t n = 0;                                   // chunks issued so far
+      for (int t = 0; t < my_tiles; ++t)
+        for (int c = 0; c < n_cycles; ++c) {
+          const int jobs = (c + 1 == n_cycles) ? JOBS - 1 : JOBS;      // the last cycle needs no next query
+          for (int j = 0; j < jobs; ++j, ++n) {
+            const uint32_t st = n % STAGES;
+            mbar_wait(&bars.w_free[st], ((n / STAGES) - 1) & 1);
+            const uint8_t* blob; uint32_t rows, row0, n_pad;
+            chunk_of(W, j, blob, rows, row0, n_pad);
+            const uint32_t plane = rows * 128u;
+            mbar_expect_tx(&bars.w_full[st], parts * 2 * plane);
+            for (int p = 0; p < parts * 2; ++p)
+              bulk_g2s(ring + st * STAGE_BYTES + p * plane, blob + ((size_t)p * n_pad + row0) * 128, plane, &bars.w_full[st]);
+          }
+        }
+    }
+    __syncwarp();
+  } else if (warp == sf::kMmaWarp) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (lane == 0) {
+      const uint32_t ring_base = smem_u32(ring);
+      uint32_t n = 0, use[2] = {0, 0}, xr = 0, tr = 0;  // chunks consumed, accumulator uses, operand phases consumed
+      for (int t = 0; t < my_tiles; ++t)
+        for (int c = 0; c < n_cycles; ++c) {
+          const int jobs = (c + 1 == n_cycles) ? JOBS - 1 : JOBS;
+          for (int j = 0; j < jobs; ++j, ++n) {
+            const uint32_t st = n % STAGES, b = (uint32_t)j & 1u;
+            if (j == 0 || j == 5) { mbar_wait(&bars.x_ready, xr & 1); ++xr; }          // X staged / X' restaged
+            if (j == 4 || j == 7 || j == 8) { mbar_wait(&bars.t_ready, tr & 1); ++tr; } // ATT / att_r / s' staged
+            mbar_wait(&bars.w_full[st], (n / STAGES) & 1);
+            mbar_wait(&bars.acc_free[b], (use[b] - 1) & 1);
+            ++use[b];
+            tc_fence_after();
+            const uint32_t bb = ring_base + st * STAGE_BYTES;
+            const uint32_t acc = b ? ACC1 : ACC0;
+            const bool from_t = (j == 4 || j >= 7);
+            if (j < 4) issue_group<NPASS, 96>(tmem_base, acc, AX_HI, AX_LO, bb, 96u * 128u, 0u);
+            else if (from_t) issue_group<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0u);
+            else issue_group<NPASS, 128>(tmem_base, acc, AX_HI, AX_LO, bb, 128u * 128u, 0u);
+            umma_commit(&bars.w_free[st]);
+            umma_commit(&bars.acc_full[b]);
+          }
+        }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ compute warps
+    const int quarter = warp & 3, hh = warp >> 2;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const int row_in_tile = quarter * 32 + lane;
+    const int up = (lane >= 30) ? 0 : lane + 1;                    // roll(h,-1)[i] = h[(i+1) mod 31]
+    const int dn = (lane == 0) ? 30 : lane - 1;                    // roll(h,+1)[i] = h[(i-1) mod 31]
+    float* my_s = &s_cur[quarter][hh * 64];
+    float* my_q = &q_cur[quarter][hh * 64];
+    float* my_attr = &attr[warp][0];
+    uint32_t use[2] = {0, 0};                                      // accumulator phases consumed
+    auto wait_acc = [&](int b) { mbar_wait(&bars.acc_full[b], use[b] & 1); ++use[b]; tc_fence_after(); };
+    auto free_acc = [&](int b) { tc_fence_before(); mbar_arrive(&bars.acc_free[b]); };
+
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int t = blockIdx.x + ti * gridDim.x;
+      const int64_t sent = (int64_t)t * 4 + quarter;
+      const uint4* kve_base = reinterpret_cast<const uint4*>(KVEI + (int64_t)t * 32768) + row_in_tile;
+      uint32_t kv[32], kvn[32];                                    // e-keys k[16] | v[16] of (row, head): current, next
+      auto load_kve = [&](int g, uint32_t* dst) {
+        const int head = 2 * g + hh;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 a = __ldg(kve_base + (head * 4 + q) * 128), c = __ldg(kve_base + (32 + head * 4 + q) * 128);
+          dst[4*q] = a.x; dst[4*q+1] = a.y; dst[4*q+2] = a.z; dst[4*q+3] = a.w;
+          dst[16+4*q] = c.x; dst[16+4*q+1] = c.y; dst[16+4*q+2] = c.z; dst[16+4*q+3] = c.w;
+        }
+      };
+      // ---- tile start: relay vectors to shared memory, X rows to tensor memory (all UMMAs of the previous tile are
+      //      complete: their last accumulator was drained below)
+      {
+        const float4* s0 = reinterpret_cast<const float4*>(S0 + sent * 128 + hh * 64);
+        const float4* q0 = reinterpret_cast<const float4*>(Q0 + sent * 128 + hh * 64);
+        if (lane < 16) reinterpret_cast<float4*>(my_s)[lane] = __ldg(s0 + lane);
+        else reinterpret_cast<float4*>(my_q)[lane - 16] = __ldg(q0 + (lane - 16));
+        __syncwarp();
+        uint32_t hi[32], lo[32];
+        if (lane == 31) split_half_row_smem(my_s, hi, lo);
+        else load_half_row(reinterpret_cast<const float4*>(XI0 + (int64_t)t * 16384) + (hh * 16) * 128 + row_in_tile, 128, hi, lo);
+        store_half_row<NPASS>(lane_addr, AX_HI, AX_LO, hh, hi, lo);
+        tc_fence_before();
+        mbar_arrive(&bars.x_ready);
+      }
+      load_kve(0, kv);
+
+      for (int c = 0; c < n_cycles; ++c) {
+        const bool last = (c + 1 == n_cycles);
+        // ================= J0..J3: satellite attention of head 2g + hh, output staged as the ATT operand
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          const int b = g & 1, head = 2 * g + hh;
+          if (g < 3) load_kve(g + 1, kvn);                          // e-keys of the next head: in flight during this one
+          wait_acc(b);
+          const uint32_t col = lane_addr + (b ? ACC1 : ACC0) + hh * 16;
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
+          {
+            float q[16], k[16];
+            tmem_ld16(col, q);
+            tmem_ld16(col + 32, k);
+            tmem_ld_wait();
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+              const float ku = __shfl_sync(0xffffffffu, k[d], up);
+              const float kd = __shfl_sync(0xffffffffu, k[d], dn);
+              const float ks = __shfl_sync(0xffffffffu, k[d], 31);
+              l0 = fmaf(q[d], ku, l0);
+              l1 = fmaf(q[d], k[d], l1);
+              l2 = fmaf(q[d], kd, l2);
+              l3 = fmaf(q[d], __uint_as_float(kv[d]), l3);
+              l4 = fmaf(q[d], ks, l4);
+            }
+          }
+          float v[16];
+          tmem_ld16(col + 64, v);
+          l0 *= 0.25f; l1 *= 0.25f; l2 *= 0.25f; l3 *= 0.25f; l4 *= 0.25f;
+          const float mx = fmaxf(fmaxf(fmaxf(l0, l1), fmaxf(l2, l3)), l4);
+          l0 = expf(l0 - mx); l1 = expf(l1 - mx); l2 = expf(l2 - mx); l3 = expf(l3 - mx); l4 = expf(l4 - mx);
+          const float inv = 1.0f / (l0 + l1 + l2 + l3 + l4);
+          l0 *= inv; l1 *= inv; l2 *= inv; l3 *= inv; l4 *= inv;
+          tmem_ld_wait();
+          free_acc(b);
+          uint32_t ohi[8], olo[8];
+#pragma unroll
+          for (int d2 = 0; d2 < 8; ++d2) {
+            float o2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int d = 2 * d2 + e;
+              const float vu = __shfl_sync(0xffffffffu, v[d], up);
+              const float vd = __shfl_sync(0xffffffffu, v[d], dn);
+              const float vs = __shfl_sync(0xffffffffu, v[d], 31);
+              float acc = l0 * vu;
+              acc = fmaf(l1, v[d], acc);
+              acc = fmaf(l2, vd, acc);
+              acc = fmaf(l3, __uint_as_float(kv[16 + d]), acc);
+              acc = fmaf(l4, vs, acc);
+              o2[e] = (lane == 31) ? 0.f : acc;                    // the relay row carries no satellite output
+            }
+            split2(o2[0], o2[1], ohi[d2], olo[d2]);
+          }
+          // head `head` covers k = 16*head .. 16*head+15 = operand columns 8*head .. 8*head+7
+          tmem_st8(lane_addr + AT_HI + head * 8, ohi);
+          if (NPASS == 3) tmem_st8(lane_addr + AT_LO + head * 8, olo);
+          if (g < 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) kv[i] = kvn[i];
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bars.t_ready);
+
+        // ================= J4: X' = relu(ATT @ Wo + b); the relay row keeps s; re-staged as the X operand
+        {
+          wait_acc(0);
+          float4* xr = last ? reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + hh * 64) : nullptr;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float v[32];
+            tmem_ld32(lane_addr + ACC0 + hh * 64 + j * 32, v);
+            tmem_ld_wait();
+            if (lane == 31) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 s4 = reinterpret_cast<const float4*>(my_s)[j * 8 + q4];
+                v[4*q4] = s4.x; v[4*q4+1] = s4.y; v[4*q4+2] = s4.z; v[4*q4+3] = s4.w;
+              }
+            } else {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_o + hh * 64 + j * 32) + q4);
+                v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
+                v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
+                v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
+                v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
+              }
+            }
+            if (xr != nullptr) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) xr[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+            }
+#pragma unroll
+            for (int q2 = 0; q2 < 16; ++q2) split2(v[2*q2], v[2*q2+1], hi[j * 16 + q2], lo[j * 16 + q2]);
+          }
+          free_acc(0);
+          store_half_row<NPASS>(lane_addr, AX_HI, AX_LO, hh, hi, lo);   // J0..J3 have completed (their commit precedes J4's)
+          tc_fence_before();
+          mbar_arrive(&bars.x_ready);
+        }
+
+        // ================= J5 (K -> ACC1), J6 (V -> ACC0): relay attention, 4 heads per warp, lane = key row
+        {
+          const float4* kv2 = reinterpret_cast<const float4*>(KV2I + sent * 8192) + (hh * 16) * 32 + lane;
+          const bool has2 = lane < n2;
+          float w1[4], w2[4];
+          wait_acc(1);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float k[16];
+            tmem_ld16(lane_addr + ACC1 + hh * 64 + h * 16, k);
+            tmem_ld_wait();
+            float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 qq = reinterpret_cast<const float4*>(my_q + h * 16)[q4];
+              d1 = fmaf(qq.x, k[4*q4], d1); d1 = fmaf(qq.y, k[4*q4+1], d1);
+              d1 = fmaf(qq.z, k[4*q4+2], d1); d1 = fmaf(qq.w, k[4*q4+3], d1);
+              if (has2) {
+                const float4 kk = __ldg(kv2 + (h * 4 + q4) * 32);
+                d2 = fmaf(qq.x, kk.x, d2); d2 = fmaf(qq.y, kk.y, d2); d2 = fmaf(qq.z, kk.z, d2); d2 = fmaf(qq.w, kk.w, d2);
+              }
+            }
+            d1 *= 0.25f;
+            d2 = has2 ? d2 * 0.25f : -3.4e38f;
+            const float mx = warp_max(fmaxf(d1, d2));
+            const float e1 = expf(d1 - mx), e2 = has2 ? expf(d2 - mx) : 0.f;
+            const float inv = 1.0f / warp_sum(e1 + e2);
+            w1[h] = e1 * inv;
+            w2[h] = e2 * inv;
+          }
+          free_acc(1);
+          wait_acc(0);
+          float p[64];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float v[16];
+            tmem_ld16(lane_addr + ACC0 + hh * 64 + h * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has2) vv = __ldg(kv2 + (32 + h * 4 + q4) * 32);
+              p[h * 16 + 4*q4]     = fmaf(w1[h], v[4*q4],     w2[h] * vv.x);
+              p[h * 16 + 4*q4 + 1] = fmaf(w1[h], v[4*q4 + 1], w2[h] * vv.y);
+              p[h * 16 + 4*q4 + 2] = fmaf(w1[h], v[4*q4 + 2], w2[h] * vv.z);
+              p[h * 16 + 4*q4 + 3] = fmaf(w1[h], v[4*q4 + 3], w2[h] * vv.w);
+            }
+          }
+          free_acc(0);
+          // reduce-scatter the 64 partial sums over the 32 lanes: lane ends with dims 2*lane, 2*lane+1
+#pragma unroll
+          for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+              const float send = upper ? p[i] : p[i + n];
+              const float keep = upper ? p[i + n] : p[i];
+              p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          *reinterpret_cast<float2*>(my_attr + 2 * lane) = make_float2(p[0], p[1]);
+          __syncwarp();
+          // att_r of this sentence / column half as the operand of J7: every lane stages the same 64 values (only the
+          // relay lane's row of the product is used)
+          uint32_t hi[32], lo[32];
+          split_half_row_smem(my_attr, hi, lo);
+          store_half_row<NPASS>(lane_addr, AT_HI, AT_LO, hh, hi, lo);   // J4 (the last reader of ATT) has completed
+          tc_fence_before();
+          mbar_arrive(&bars.t_ready);
+          __syncwarp();
+        }
+
+        // ================= J7: s' = relu(att_r @ Wo_relay + b) on the relay lane; operand of J8; relay row of X patched
+        {
+          wait_acc(1);
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float v[32];
+            tmem_ld32(lane_addr + ACC1 + hh * 64 + j * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_r + hh * 64 + j * 32) + q4);
+              v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
+              v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
+              v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
+              v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
+            }
+            if (lane == 31) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4)
+                reinterpret_cast<float4*>(my_s)[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+              if (last) {
+                float4* xr = reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + hh * 64);
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) xr[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+              }
+            }
+#pragma unroll
+            for (int q2 = 0; q2 < 16; ++q2) split2(v[2*q2], v[2*q2+1], hi[j * 16 + q2], lo[j * 16 + q2]);
+          }
+          free_acc(1);
+          if (!last) {
+            store_half_row<NPASS>(lane_addr, AT_HI, AT_LO, hh, hi, lo);      // operand of J8 (J7 has completed)
+            tc_fence_before();
+            mbar_arrive(&bars.t_ready);
+            // patch the relay row of the X operand with s' (J5/J6, the last readers of X', have completed): every lane
+            // rewrites its own row unchanged, the relay lane substitutes the new words
+#pragma unroll
+            for (int c4 = 0; c4 < 2; ++c4) {
+              uint32_t w[16];
+              tmem_ld16(lane_addr + AX_HI + hh * 32 + c4 * 16, reinterpret_cast<float*>(w));
+              tmem_ld_wait();
+              if (lane == 31) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = hi[c4 * 16 + i];
+              }
+              tmem_st16(lane_addr + AX_HI + hh * 32 + c4 * 16, w);
+              if (NPASS == 3) {
+                tmem_ld16(lane_addr + AX_LO + hh * 32 + c4 * 16, reinterpret_cast<float*>(w));
+                tmem_ld_wait();
+                if (lane == 31) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) w[i] = lo[c4 * 16 + i];
+                }
+                tmem_st16(lane_addr + AX_LO + hh * 32 + c4 * 16, w);
+              }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars.x_ready);
+            load_kve(0, kv);                                             // e-keys of the next cycle's first head
+            // ================= J8: q' = s' @ Wq_relay on the relay lane
+            wait_acc(0);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              float v[32];
+              tmem_ld32(lane_addr + ACC0 + hh * 64 + j * 32, v);
+              tmem_ld_wait();
+              if (lane == 31) {
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4)
+                  reinterpret_cast<float4*>(my_q)[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+              }
+            }
+            free_acc(0);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == sf::kMmaWarp) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace dsc
+
+using namespace dsc;
+
+template <int NPASS>
+static int launch_star_fused(const float* xi0, const float* s0, const float* q0, const float* kvei, const float* kv2i, int n2,
+                             const sf::Weights& w, const float* bias_o, const float* bias_r, float* xrow, int n_tiles,
+                             int n_cycles, cudaStream_t s) {
+  constexpr size_t smem = (size_t)sf::STAGES * sf::STAGE_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(star_fused_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("dsc_star_cycles_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
+  const int grid = n_tiles < kSMs ? n_tiles : kSMs;
+  star_fused_kernel<NPASS><<<grid, sf::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles);
+  return check_launch("dsc_star_cycles_tc");
+}
+
+extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, const float* kv_e,
+                                  const float* kv2, int n2,
+                                  const void* packed_wqkv_grouped, const void* packed_wo, const void* packed_wkv_relay,
+                                  const void* packed_wo_relay, const void* packed_wq_relay,
+                                  const float* bias_o, const float* bias_o_relay,
+                                  float* x_rowmajor, int n_sent, int n_cycles, int prec, void* stream) {
+  DSC_REQUIRE(x_tile0 && s0 && q0 && kv_e && packed_wqkv_grouped && packed_wo && packed_wkv_relay && packed_wo_relay &&
+              packed_wq_relay && bias_o && bias_o_relay && x_rowmajor, "dsc_star_cycles_tc: null pointer");
+  DSC_REQUIRE(n_sent >= 0 && (n_sent % 4) == 0 && n_cycles >= 1, "dsc_star_cycles_tc: n_sent must be a multiple of 4, n_cycles >= 1");
+  DSC_REQUIRE(n2 >= 0 && n2 <= 32 && (n2 == 0 || kv2), "dsc_star_cycles_tc: bad h2 key count");
+  DSC_REQUIRE(aligned16(x_tile0) && aligned16(s0) && aligned16(q0) && aligned16(kv_e) && (!kv2 || aligned16(kv2)) &&
+              aligned16(bias_o) && aligned16(bias_o_relay) && aligned16(x_rowmajor), "dsc_star_cycles_tc: misaligned pointer");
+  DSC_REQUIRE((((uintptr_t)packed_wqkv_grouped | (uintptr_t)packed_wo | (uintptr_t)packed_wkv_relay | (uintptr_t)packed_wo_relay |
+                (uintptr_t)packed_wq_relay) & 127u) == 0, "dsc_star_cycles_tc: packed weights must be 128-byte aligned");
+  DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_cycles_tc: prec must be 1 (bf16x3) or 2 (bf16)");
+  if (n_sent == 0) return DSC_OK;
+  if (n2 == 0) kv2 = kv_e;        // never dereferenced (lane < n2 is false); keeps the pointer arithmetic defined
+  sf::Weights w{reinterpret_cast<const uint8_t*>(packed_wqkv_grouped), reinterpret_cast<const uint8_t*>(packed_wo),
+                reinterpret_cast<const uint8_t*>(packed_wkv_relay), reinterpret_cast<const uint8_t*>(packed_wo_relay),
+                reinterpret_cast<const uint8_t*>(packed_wq_relay)};
+  return prec == 1 ? launch_star_fused<3>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, as_stream(stream))
+                   : launch_star_fused<1>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, as_stream(stream));
+}

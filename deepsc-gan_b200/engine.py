@@ -51,7 +51,8 @@ def transmit(net, inp: torch.Tensor, n_units: int, n_std: torch.Tensor, *, chann
         x = _lib.power_normalize(u, n_units, 1.0, sumsq=sumsq)
         g = net.generator.raw(x).contiguous()
         elems = g.numel() // n_units
-        ps = n_std * (math.sqrt(10 ** (PNR_dB / 10)) * math.sqrt(float(elems)))
+        # per-unit scale of the unit-norm perturbation; a caller that fixes the perturbation-to-signal ratio passes it
+        ps = p_scale if p_scale is not None else n_std * (math.sqrt(10 ** (PNR_dB / 10)) * math.sqrt(float(elems)))
         y, _ = _lib.channel(x, n_units, n_std, noise=noise, seed=seed, offset=offset, p=g,
                             p_sumsq=_lib.unit_sumsq(g, n_units), p_factor=float(elems), p_scale=ps.contiguous())
         return x, y
@@ -97,7 +98,7 @@ class StarGreedyDecoder:
         mem = net.channel_decoder.call(received)                      # hoisted out of the step loop
         st0 = self.layers[0]
         _lib.star_pack(mem.contiguous(), st0.tile)
-        prepare_kv_e(st0.tile, st0.layer.multi_att_satellite, st0.ws)
+        prepare_kv_e(st0.tile, st0.layer.multi_att_satellite, st0.ws, st0.relay)
         tc = use_tc(S)
         self.outputs.zero_()
         self.outputs[:, 0] = start_idx

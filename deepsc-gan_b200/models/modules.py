@@ -21,6 +21,7 @@ SURVEY.md K17), out of place, so that ``utlis`` can take d(loss)/d(symbols) and 
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -32,6 +33,9 @@ from .. import autograd as AG
 
 D_MODEL = 128
 PREC = 0   # precision knob passed to dsc_linear: 0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16
+# tcgen05 star cycles: True = all cycles of a layer in one persistent launch (dsc_star_cycles_tc),
+# False = two fused launches per cycle (dsc_star_sat_tc + dsc_star_mix_tc) plus the relay update
+STAR_FUSED = os.environ.get("DSC_STAR_FUSED", "1") != "0"
 
 
 def set_precision(prec: int) -> None:
@@ -270,6 +274,8 @@ class StarWorkspace:
         self.s_buf = torch.empty((n_sent, 128), **f)        # relay nodes (tcgen05 path)
         self.kvei = None                                    # interleaved k|v of the e rows (tcgen05 path)
         self.kv2i = None                                    # interleaved h2 cache built from a row-major kv2
+        self.xi0 = None                                     # interleaved e tile, s0 and q0 = s0 @ wq_relay: the
+        self.s0 = self.q0 = None                            # cycle-0 state of the one-launch kernel (constant per e tile)
 
     def tc_buffers(self):
         if self.kvei is None:
@@ -282,12 +288,20 @@ def use_tc(n_sent: int) -> bool:
     return PREC != 0 and n_sent % 4 == 0
 
 
-def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace) -> None:
-    """k|v of the e rows under the satellite weights (constant over cycles and greedy steps)."""
+def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace, relay: Optional[sublayer1] = None) -> None:
+    """Everything that depends on the e tile only (constant over cycles and greedy steps): k|v of the e rows under the
+    satellite weights and, for the one-launch tcgen05 kernel, the interleaved e tile, s0 and q0 = s0 @ wq_relay."""
     S = e_tile.shape[0]
     _lib.linear(e_tile.view(S * 32, 128), sat._packed("kv"), None, out=ws.kv_e, prec=PREC)
     if use_tc(S):
         _lib.star_interleave(ws.kv_e.view(S // 4, 128, 256), ws.tc_buffers(), 128)
+        if STAR_FUSED and relay is not None:
+            f = dict(device=e_tile.device, dtype=torch.float32)
+            if ws.xi0 is None:
+                ws.xi0, ws.s0, ws.q0 = torch.empty((S * 4096,), **f), torch.empty((S, 128), **f), torch.empty((S, 128), **f)
+            _lib.star_interleave(e_tile.view(S // 4, 128, 128), ws.xi0, 128)
+            ws.s0.copy_(e_tile[:, 31, :])
+            _lib.linear(ws.s0, relay.wq.kernel.detach(), None, out=ws.q0, prec=PREC)
 
 
 def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_num: int,
@@ -305,7 +319,16 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
     if ws is None:
         ws = StarWorkspace(S, e_tile.device)
     if not kv_e_ready:
-        prepare_kv_e(e_tile, sat, ws)
+        prepare_kv_e(e_tile, sat, ws, relay)
+    if use_tc(S) and STAR_FUSED:
+        if n2 > 0 and kv2i is None:
+            pad = torch.zeros((S, 32, 256), device=e_tile.device, dtype=torch.float32)
+            pad[:, : kv2.shape[1]] = kv2
+            kv2i = _lib.star_interleave(pad, torch.empty_like(pad).view(-1), 32)
+        return _lib.star_cycles_tc(ws.xi0, ws.s0, ws.q0, ws.kvei, kv2i, n2, sat._packed("qkv_grouped"),
+                                   sat.dense.kernel.detach(), relay._packed("kv"), relay.dense.kernel.detach(),
+                                   relay.wq.kernel.detach(), sat.dense.bias.detach(), relay.dense.bias.detach(),
+                                   ws.x, S, cycle_num, PREC)
     if use_tc(S):
         # tcgen05 path: two fused persistent kernels per cycle (projection + satellite attention; dense + relay
         # k|v projection + relay attention) plus the two per-sentence Dense calls of the relay node.

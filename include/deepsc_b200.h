@@ -120,6 +120,20 @@ int dsc_star_mix_tc(const float* att, float* x_tile, float* x_rowmajor, const fl
                     const float* bias_o, const float* q_relay, const float* kv2, int n2,
                     float* att_relay, int n_sent, int prec, void* stream);
 
+/* K2+K3+K4, all cycles in one launch: the loop of models/modules.py:287-306 / 360-378 with the tile state (X, ATT, s, q)
+ * resident in tensor / shared memory and the weights streamed from L2 through a shared-memory ring.
+ * x_tile0 [n_sent/4][32][128][4] = the e tile (cycle-0 node states, interleaved); s0 [n_sent,128] = mean row;
+ * q0 [n_sent,128] = s0 @ wq_relay; kv_e, kv2, n2 as in dsc_star_sat_tc / dsc_star_mix_tc; the five packed weights are
+ * dsc_pack_weight images of the grouped [128,384] satellite projection, wo_satellite, [wk|wv]_relay, wo_relay, wq_relay
+ * (pass the satellite matrices again for the layers that drive the relay with the satellite weights, :175, :243).
+ * x_rowmajor [n_sent][32][128] receives the tile after n_cycles cycles (rows 0..30 = h, row 31 = s). */
+int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, const float* kv_e,
+                       const float* kv2, int n2,
+                       const void* packed_wqkv_grouped, const void* packed_wo, const void* packed_wkv_relay,
+                       const void* packed_wo_relay, const void* packed_wq_relay,
+                       const float* bias_o, const float* bias_o_relay,
+                       float* x_rowmajor, int n_sent, int n_cycles, int prec, void* stream);
+
 /* relay node update: s_out = relu(att_relay @ wo + bo) (models/modules.py:305-306), q_out = s_out @ wq (the next
  * cycle's relay query).  fp32 FFMA, weights Keras layout [128,128] contiguous, all tensors [n_sent,128]. */
 int dsc_star_relay_update(const float* att_relay, const float* wo, const float* bo, const float* wq,
