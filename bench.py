@@ -13,7 +13,8 @@ the int32 BLEU count table is all-gathered at the end of every step.
 value   : inputs resident in HBM, CUDA-event time, max over ranks.
 e2e     : same metric through the public API with HOST buffers: per step the ids are copied from pinned host
           memory and the BLEU counts are read back, both inside the timed region.
-roofline: the dominant kernel (star_sat_kernel, HBM-bound per-cycle launch), algorithmic bytes per launch / mean event-timed launch.
+roofline: the dominant kernel (star_fused_kernel: 8 star cycles per launch, tensor-pipe bound), algorithmic FLOPs x 3 bf16 passes
+          per launch / mean event-timed launch, against the measured bf16 peak.
 cpu_baseline / --impl reference: the CPU oracle (PyTorch restatement of the reference; the TensorFlow reference
           itself cannot run here) on a bounded sample of the same workload, all host threads.
 """
@@ -36,9 +37,9 @@ import torch
 METRIC = "sentences/sec for SNR-sweep encode->channel->decode+BLEU"
 UNIT = "sentences/s"
 SNRS = list(range(19))
-# dram__bytes_read.sum + dram__bytes_write.sum of one star_sat_kernel<3> launch from the `ncu --set full` capture
-# summarised in profiles/ (keyed by sentences per launch); null when no capture exists for the size that ran
-ROOFLINE_TRAFFIC_BYTES = {2368: 117852416 + 19215872}
+# dram__bytes_read.sum + dram__bytes_write.sum of one star_fused_kernel<3> launch (8 cycles) from the `ncu --set full`
+# capture summarised in profiles/ (keyed by sentences per launch); null when no capture exists for the size that ran
+ROOFLINE_TRAFFIC_BYTES = {}
 
 
 def load_peaks():
@@ -230,25 +231,44 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms, t_e2e_ms = float(tt[0]), float(tt[1])
 
-    # ---- roofline of the dominant kernel: star_sat_kernel (fused QKV projection + satellite attention) ----------
-    # HBM-bound as launched per cycle: per sentence it reads the 31 node rows + relay row (32 x 512 B), the k|v of the
-    # 31 e rows (31 x 1024 B) and writes 31 attention rows (31 x 512 B) = 64,000 algorithmic bytes.
-    SAT_BYTES_PER_SENTENCE = 32 * 512 + 31 * 1024 + 31 * 512
-    dom = [(a.elapsed_time(b), meta) for op, a, b, meta in prof if op == "dsc_star_sat_tc" and meta == S]
+    # ---- roofline of the dominant kernel -------------------------------------------------------------------
+    # star_fused_kernel (dsc_star_cycles_tc): all 8 cycles of a star layer in one launch, tile state in TMEM/smem, so
+    # it is bound by the tensor pipe, not HBM.  Algorithmic FLOPs per sentence and cycle:
+    #   32 rows x 128 x (384 [Wq|Wk|Wv]_sat + 128 Wo_sat + 256 [Wk|Wv]_relay) x 2  +  2 relay GEMVs x 128 x 128 x 2
+    # Every fp32-class product costs three bf16 UMMA passes (bf16x3), so `achieved` counts 3 tensor FLOPs per
+    # algorithmic FLOP and is compared with the measured bf16 peak (sustained: the kernel is timed inside a long step).
+    FLOPS_PER_SENT_CYCLE = 32 * 128 * (384 + 128 + 256) * 2 + 2 * 128 * 128 * 2
+    passes = {1: 3, 2: 1}.get(args.prec, 0)
+    dom = [(a.elapsed_time(b), meta) for op, a, b, meta in prof if op == "dsc_star_cycles_tc" and meta[0] == S]
     roof = None
-    if dom:
+    if dom and passes:
         mean_ms = sum(t for t, _ in dom) / len(dom)
-        nbytes = float(SAT_BYTES_PER_SENTENCE) * S
-        achieved = nbytes / (mean_ms * 1e-3) / 1e9
-        peak = peaks["hbm_gbs"]
-        roof = {"bound": "hbm", "kernel": "star_sat_kernel<3> via dsc_star_sat_tc (QKV projection on tcgen05 + satellite "
-                                          "attention, one launch per star cycle)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        cycles = dom[0][1][1]
+        flops = float(FLOPS_PER_SENT_CYCLE) * S * cycles
+        achieved = passes * flops / (mean_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {"bound": "tensor", "kernel": "star_fused_kernel<3> via dsc_star_cycles_tc (8 star cycles per launch: QKV / Wo / relay "
+                                             "K|V / relay update UMMAs + satellite and relay attention, state in TMEM)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": ROOFLINE_TRAFFIC_BYTES.get(S),
-                "peak_source": f"{peaks['source']} HBM copy bandwidth (MEASURED_PEAKS.json hbm_gbs)",
-                "launches_timed": len(dom), "mean_launch_ms": mean_ms, "bytes_per_launch": nbytes,
+                "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json bf16_tflops_sustained)",
+                "launches_timed": len(dom), "mean_launch_ms": mean_ms, "algorithmic_flops_per_launch": flops,
+                "tensor_passes_per_flop": passes, "algorithmic_tflops": flops / (mean_ms * 1e-3) / 1e12,
                 "share_of_step": sum(t for t, _ in dom) / t_ms,
-                "arith": {1: "bf16x3 tcgen05, fp32 accumulate/softmax", 2: "bf16 tcgen05"}.get(args.prec, "fp32")}
+                "arith": {1: "bf16x3 tcgen05 (3 bf16 UMMA passes per fp32-class product), fp32 accumulate/softmax",
+                          2: "bf16 tcgen05"}[args.prec]}
+    elif prof:
+        # per-cycle kernels (DSC_STAR_FUSED=0): star_sat_kernel is HBM-bound, 64,000 algorithmic bytes per sentence
+        SAT_BYTES_PER_SENTENCE = 32 * 512 + 31 * 1024 + 31 * 512
+        dom = [(a.elapsed_time(b), meta) for op, a, b, meta in prof if op == "dsc_star_sat_tc" and meta == S]
+        if dom:
+            mean_ms = sum(t for t, _ in dom) / len(dom)
+            nbytes = float(SAT_BYTES_PER_SENTENCE) * S
+            achieved = nbytes / (mean_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": "star_sat_kernel<3> via dsc_star_sat_tc (one launch per star cycle)",
+                    "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                    "traffic": None, "peak_source": f"{peaks['source']} HBM copy bandwidth", "launches_timed": len(dom),
+                    "mean_launch_ms": mean_ms, "bytes_per_launch": nbytes, "share_of_step": sum(t for t, _ in dom) / t_ms}
 
     if rank != 0:
         if world > 1:
