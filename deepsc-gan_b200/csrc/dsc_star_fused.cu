@@ -18,6 +18,11 @@
 // are don't-care.  Accumulators alternate between two 128-column TMEM buffers (J7 -> buffer 0, J8 -> buffer 1), so the UMMA of job j+1 overlaps the
 // epilogue of job j wherever the data dependence allows (all of J0..J3, J5/J6, and J0 of the next cycle under J8).
 //
+// Tried and dropped (round 1): keeping TWO tiles per CTA on the same 8 compute warps (ATT held in registers, relay GEMV
+// operands patched into the X operand, accumulators ping-ponged between the tiles).  Correct, but 1.9x slower: the
+// kernel is bound by the latency of the register-side work (tcgen05.ld -> shuffles -> tcgen05.st chains at 2 warps per
+// scheduler), not by UMMA latency, and the extra live state spilled.  The next step is more compute warps per tile.
+//
 // Warps: 0-7 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, hh = warp >> 2 the column half),
 // 8 = UMMA issuer, 9 = weight producer.  Arithmetic as in dsc_star_tc.cu: prec 1 = bf16x3, 2 = bf16; fp32 softmax.
 #include "dsc_star_common.cuh"
@@ -466,498 +471,6 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
 }
 
 
-// ============================================================================================================
-// Pair-interleaved variant: a CTA works on TWO tiles at a time so that the UMMA + hand-off latency of one tile hides
-// behind the register-side work of the other, and every streamed weight chunk (except the QKV groups) feeds both.
-//   TMEM: two accumulators ACC0 / ACC1 (128 columns each) and one A operand per tile slot AX(T) (hi 64 + lo 64).
-//   There is no separate ATT operand: the satellite attention output is held in registers during the tile's QKV
-//   phase and stored into AX(T) once the last QKV UMMA has completed (X is dead then); the relay GEMVs J7 / J8 read
-//   AX(T) too, with the relay row patched to att_r and then to s' (the other rows of those products are don't-care).
-//   Job order per pair and cycle (accumulator in brackets):
-//     J0..J3 of slot 0 [0,1,0,1], J0..J3 of slot 1 [0,1,0,1]      (QKV phase of one tile double-buffers over BOTH)
-//     J4(0)[0] J4(1)[1]  J5(0)[0] J5(1)[1]  J6(0)[0] J6(1)[1]  J7(0)[0] J7(1)[1]  J8(0)[0] J8(1)[1]
-//   so outside the QKV phase slot T owns accumulator T and the two slots ping-pong.
-// ============================================================================================================
-namespace sf2 {
-constexpr int kCompute = 8, kMmaWarp = 8, kProdWarp = 9, kThreads = 320;
-constexpr int STAGES = 3;
-constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;
-constexpr uint32_t ACC0 = 0, ACC1 = 128;
-__host__ __device__ constexpr uint32_t ax_hi(int T) { return 256u + 128u * (uint32_t)T; }
-__host__ __device__ constexpr uint32_t ax_lo(int T) { return 320u + 128u * (uint32_t)T; }
-struct Bars {
-  uint64_t w_full[STAGES], w_free[STAGES];
-  uint64_t acc_full[2], acc_free[2];
-  uint64_t x_ready[2];                      // per slot: the A operand AX(T) has been (re)written for the next job
-};
-}  // namespace sf2
-
-template <int NPASS>
-__global__ void __launch_bounds__(sf2::kThreads, 1)
-star_fused2_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, const float* __restrict__ Q0,
-                   const float* __restrict__ KVEI, const float* __restrict__ KV2I, int n2, sf::Weights W,
-                   const float* __restrict__ bias_o, const float* __restrict__ bias_r,
-                   float* __restrict__ Xrow, int n_tiles, int n_cycles) {
-  using namespace sf2;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) sf2::Bars bars;
-  __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(16) float s_cur[2][4][128];
-  __shared__ __align__(16) float q_cur[2][4][128];
-  __shared__ __align__(16) float attr[2][8][64];
-  constexpr int parts = (NPASS == 3) ? 2 : 1;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_free[s], 1); }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kCompute * 32);
-      mbar_init(&bars.x_ready[b], kCompute * 32);
-    }
-    fence_barrier_init();
-  }
-  if (warp == sf2::kMmaWarp) tmem_alloc<512>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-  const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int n_pairs = (my_tiles + 1) / 2;
-
-  if (warp == sf2::kProdWarp) {
-    // ------------------------------------------------------------------ weight producer
-    if (lane == 0) {
-      uint32_t n = 0;
-      auto put = [&](int j) {
-        const uint32_t st = n % STAGES;
-        mbar_wait(&bars.w_free[st], ((n / STAGES) - 1) & 1);
-        const uint8_t* blob; uint32_t rows, row0, n_pad;
-        sf::chunk_of(W, j, blob, rows, row0, n_pad);
-        const uint32_t plane = rows * 128u;
-        mbar_expect_tx(&bars.w_full[st], parts * 2 * plane);
-        for (int p = 0; p < parts * 2; ++p)
-          bulk_g2s(ring + st * STAGE_BYTES + p * plane, blob + ((size_t)p * n_pad + row0) * 128, plane, &bars.w_full[st]);
-        ++n;
-      };
-      for (int pr = 0; pr < n_pairs; ++pr) {
-        const int nT = (2 * pr + 1 < my_tiles) ? 2 : 1;
-        for (int c = 0; c < n_cycles; ++c) {
-          for (int T = 0; T < nT; ++T)
-            for (int j = 0; j < 4; ++j) put(j);                     // the QKV groups are streamed once per slot
-          const int jobs = (c + 1 == n_cycles) ? 8 : 9;
-          for (int j = 4; j < jobs; ++j) put(j);                    // one chunk feeds both slots
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == sf2::kMmaWarp) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
-      const uint32_t ring_base = smem_u32(ring);
-      uint32_t n = 0, use0 = 0, use1 = 0, xr0 = 0, xr1 = 0;
-      auto wait_stage = [&]() { mbar_wait(&bars.w_full[n % STAGES], (n / STAGES) & 1); };
-      auto free_stage = [&]() { umma_commit(&bars.w_free[n % STAGES]); ++n; };
-      auto wait_x = [&](int T) {
-        if (T) { mbar_wait(&bars.x_ready[1], xr1 & 1); ++xr1; } else { mbar_wait(&bars.x_ready[0], xr0 & 1); ++xr0; }
-      };
-      auto take_acc = [&](int b) {
-        if (b) { mbar_wait(&bars.acc_free[1], (use1 - 1) & 1); ++use1; } else { mbar_wait(&bars.acc_free[0], (use0 - 1) & 1); ++use0; }
-        tc_fence_after();
-      };
-      for (int pr = 0; pr < n_pairs; ++pr) {
-        const int nT = (2 * pr + 1 < my_tiles) ? 2 : 1;
-        for (int c = 0; c < n_cycles; ++c) {
-          // ---- QKV phase, slot by slot
-          for (int T = 0; T < nT; ++T) {
-            if (c == 0) wait_x(T);                                   // X staged at tile start (later cycles: the patch
-            for (int g = 0; g < 4; ++g) {                            //  was already waited for by J8 of the previous cycle)
-              wait_stage();
-              take_acc(g & 1);
-              issue_group<NPASS, 96>(tmem_base, (g & 1) ? ACC1 : ACC0, ax_hi(T), ax_lo(T), ring_base + (n % STAGES) * STAGE_BYTES,
-                                     96u * 128u, 0u);
-              free_stage();
-              umma_commit(&bars.acc_full[g & 1]);
-            }
-          }
-          // ---- J4..J8: one chunk, both slots (slot T -> accumulator T)
-          const int jobs = (c + 1 == n_cycles) ? 8 : 9;
-          for (int j = 4; j < jobs; ++j) {
-            wait_stage();
-            for (int T = 0; T < nT; ++T) {
-              if (j != 6) wait_x(T);                                 // att / X' / att_r / s' written into AX(T); J6 reuses X'
-              take_acc(T);
-              issue_group<NPASS, 128>(tmem_base, T ? ACC1 : ACC0, ax_hi(T), ax_lo(T), ring_base + (n % STAGES) * STAGE_BYTES,
-                                      128u * 128u, 0u);
-              umma_commit(&bars.acc_full[T]);
-            }
-            free_stage();
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ compute warps
-    const int quarter = warp & 3, hh = warp >> 2;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    const int row_in_tile = quarter * 32 + lane;
-    const int up = (lane >= 30) ? 0 : lane + 1;
-    const int dn = (lane == 0) ? 30 : lane - 1;
-    uint32_t use0 = 0, use1 = 0;
-    auto wait_acc = [&](int b) {
-      if (b) { mbar_wait(&bars.acc_full[1], use1 & 1); ++use1; } else { mbar_wait(&bars.acc_full[0], use0 & 1); ++use0; }
-      tc_fence_after();
-    };
-    auto free_acc = [&](int b) { tc_fence_before(); mbar_arrive(&bars.acc_free[b]); };
-    auto x_done = [&](int T) { tmem_st_wait(); tc_fence_before(); mbar_arrive(&bars.x_ready[T]); };
-    // patch the relay lane's half row of AX(T) with the words hi/lo (every lane rewrites its own row unchanged)
-    auto patch_relay_row = [&](int T, const uint32_t* hi, const uint32_t* lo) {
-#pragma unroll
-      for (int c4 = 0; c4 < 2; ++c4) {
-        uint32_t w[16];
-        tmem_ld16(lane_addr + ax_hi(T) + hh * 32 + c4 * 16, reinterpret_cast<float*>(w));
-        tmem_ld_wait();
-        if (lane == 31) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) w[i] = hi[c4 * 16 + i];
-        }
-        tmem_st16(lane_addr + ax_hi(T) + hh * 32 + c4 * 16, w);
-        if (NPASS == 3) {
-          tmem_ld16(lane_addr + ax_lo(T) + hh * 32 + c4 * 16, reinterpret_cast<float*>(w));
-          tmem_ld_wait();
-          if (lane == 31) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] = lo[c4 * 16 + i];
-          }
-          tmem_st16(lane_addr + ax_lo(T) + hh * 32 + c4 * 16, w);
-        }
-      }
-    };
-
-    for (int pr = 0; pr < n_pairs; ++pr) {
-      const int nT = (2 * pr + 1 < my_tiles) ? 2 : 1;
-      const int t0 = blockIdx.x + (2 * pr) * gridDim.x;              // tile of slot T = t0 + T * gridDim.x
-      auto tile_of = [&](int T) { return t0 + T * (int)gridDim.x; };
-      uint32_t kv[32], kvn[32];
-      auto load_kve = [&](int T, int g, uint32_t* dst) {
-        const uint4* base = reinterpret_cast<const uint4*>(KVEI + (int64_t)tile_of(T) * 32768) + row_in_tile;
-        const int head = 2 * g + hh;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 a = __ldg(base + (head * 4 + q) * 128), c = __ldg(base + (32 + head * 4 + q) * 128);
-          dst[4*q] = a.x; dst[4*q+1] = a.y; dst[4*q+2] = a.z; dst[4*q+3] = a.w;
-          dst[16+4*q] = c.x; dst[16+4*q+1] = c.y; dst[16+4*q+2] = c.z; dst[16+4*q+3] = c.w;
-        }
-      };
-      // ---- pair start: relay vectors to shared memory, X rows to tensor memory
-#pragma unroll
-      for (int T = 0; T < 2; ++T) {
-        if (T < nT) {
-          const int64_t sent = (int64_t)tile_of(T) * 4 + quarter;
-          float* my_s = &s_cur[T][quarter][hh * 64];
-          float* my_q = &q_cur[T][quarter][hh * 64];
-          const float4* s0 = reinterpret_cast<const float4*>(S0 + sent * 128 + hh * 64);
-          const float4* q0 = reinterpret_cast<const float4*>(Q0 + sent * 128 + hh * 64);
-          if (lane < 16) reinterpret_cast<float4*>(my_s)[lane] = __ldg(s0 + lane);
-          else reinterpret_cast<float4*>(my_q)[lane - 16] = __ldg(q0 + (lane - 16));
-          __syncwarp();
-          uint32_t hi[32], lo[32];
-          if (lane == 31) split_half_row_smem(my_s, hi, lo);
-          else load_half_row(reinterpret_cast<const float4*>(XI0 + (int64_t)tile_of(T) * 16384) + (hh * 16) * 128 + row_in_tile, 128, hi, lo);
-          store_half_row<NPASS>(lane_addr, ax_hi(T), ax_lo(T), hh, hi, lo);
-          tc_fence_before();
-          mbar_arrive(&bars.x_ready[T]);
-        }
-      }
-      load_kve(0, 0, kv);
-
-      for (int c = 0; c < n_cycles; ++c) {
-        const bool last = (c + 1 == n_cycles);
-        // ================= QKV phase: slot 0 then slot 1; attention output of the 4 head pairs held in registers
-#pragma unroll
-        for (int T = 0; T < 2; ++T) {
-          if (T < nT) {
-            uint32_t att_hi[4][8], att_lo[4][8];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int b = g & 1;
-              if (g < 3) load_kve(T, g + 1, kvn);
-              else if (T + 1 < nT) load_kve(T + 1, 0, kvn);
-              wait_acc(b);
-              const uint32_t col = lane_addr + (b ? ACC1 : ACC0) + hh * 16;
-              float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
-              {
-                float q[16], k[16];
-                tmem_ld16(col, q);
-                tmem_ld16(col + 32, k);
-                tmem_ld_wait();
-#pragma unroll
-                for (int d = 0; d < 16; ++d) {
-                  const float ku = __shfl_sync(0xffffffffu, k[d], up);
-                  const float kd = __shfl_sync(0xffffffffu, k[d], dn);
-                  const float ks = __shfl_sync(0xffffffffu, k[d], 31);
-                  l0 = fmaf(q[d], ku, l0);
-                  l1 = fmaf(q[d], k[d], l1);
-                  l2 = fmaf(q[d], kd, l2);
-                  l3 = fmaf(q[d], __uint_as_float(kv[d]), l3);
-                  l4 = fmaf(q[d], ks, l4);
-                }
-              }
-              float v[16];
-              tmem_ld16(col + 64, v);
-              l0 *= 0.25f; l1 *= 0.25f; l2 *= 0.25f; l3 *= 0.25f; l4 *= 0.25f;
-              const float mx = fmaxf(fmaxf(fmaxf(l0, l1), fmaxf(l2, l3)), l4);
-              l0 = expf(l0 - mx); l1 = expf(l1 - mx); l2 = expf(l2 - mx); l3 = expf(l3 - mx); l4 = expf(l4 - mx);
-              const float inv = 1.0f / (l0 + l1 + l2 + l3 + l4);
-              l0 *= inv; l1 *= inv; l2 *= inv; l3 *= inv; l4 *= inv;
-              tmem_ld_wait();
-              free_acc(b);
-#pragma unroll
-              for (int d2 = 0; d2 < 8; ++d2) {
-                float o2[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                  const int d = 2 * d2 + e;
-                  const float vu = __shfl_sync(0xffffffffu, v[d], up);
-                  const float vd = __shfl_sync(0xffffffffu, v[d], dn);
-                  const float vs = __shfl_sync(0xffffffffu, v[d], 31);
-                  float acc = l0 * vu;
-                  acc = fmaf(l1, v[d], acc);
-                  acc = fmaf(l2, vd, acc);
-                  acc = fmaf(l3, __uint_as_float(kv[16 + d]), acc);
-                  acc = fmaf(l4, vs, acc);
-                  o2[e] = (lane == 31) ? 0.f : acc;
-                }
-                split2(o2[0], o2[1], att_hi[g][d2], att_lo[g][d2]);
-              }
-              if (g < 3 || T + 1 < nT) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) kv[i] = kvn[i];
-              }
-            }
-            // J3 of this slot has completed (its accumulator was just drained), so X is dead: ATT takes its place.
-            // head 2g + hh covers k = 16*head .. +15 = operand columns 8*head .. +7
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              tmem_st8(lane_addr + ax_hi(T) + (2 * g + hh) * 8, att_hi[g]);
-              if (NPASS == 3) tmem_st8(lane_addr + ax_lo(T) + (2 * g + hh) * 8, att_lo[g]);
-            }
-            x_done(T);
-          }
-        }
-
-        // ================= J4: X' = relu(ATT @ Wo + b); the relay row keeps s; re-staged as the X operand
-#pragma unroll
-        for (int T = 0; T < 2; ++T) {
-          if (T < nT) {
-            const float* my_s = &s_cur[T][quarter][hh * 64];
-            wait_acc(T);
-            float4* xr = last ? reinterpret_cast<float4*>(Xrow + ((int64_t)tile_of(T) * 128 + row_in_tile) * 128 + hh * 64) : nullptr;
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              float v[32];
-              tmem_ld32(lane_addr + (T ? ACC1 : ACC0) + hh * 64 + j * 32, v);
-              tmem_ld_wait();
-              if (lane == 31) {
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                  const float4 s4 = reinterpret_cast<const float4*>(my_s)[j * 8 + q4];
-                  v[4*q4] = s4.x; v[4*q4+1] = s4.y; v[4*q4+2] = s4.z; v[4*q4+3] = s4.w;
-                }
-              } else {
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_o + hh * 64 + j * 32) + q4);
-                  v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
-                  v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
-                  v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
-                  v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
-                }
-              }
-              if (xr != nullptr) {
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) xr[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-              }
-#pragma unroll
-              for (int q2 = 0; q2 < 16; ++q2) split2(v[2*q2], v[2*q2+1], hi[j * 16 + q2], lo[j * 16 + q2]);
-            }
-            free_acc(T);
-            store_half_row<NPASS>(lane_addr, ax_hi(T), ax_lo(T), hh, hi, lo);      // J4 has completed: ATT is dead
-            tc_fence_before();
-            mbar_arrive(&bars.x_ready[T]);
-          }
-        }
-
-        // ================= J5 (K), J6 (V): relay attention, 4 heads per warp, lane = key row.  The h2 keys / values of
-        // the lane's row stream through ONE register buffer, always a phase ahead: k2(0) -> k2(1) -> v2(0) -> v2(1).
-        float4 kv2r[16];
-        float w1[2][4], w2[2][4];
-        const bool has2 = lane < n2;
-        auto kv2_ptr = [&](int T, int part) {
-          return reinterpret_cast<const float4*>(KV2I + ((int64_t)tile_of(T) * 4 + quarter) * 8192) + (hh * 16 + part * 32) * 32 + lane;
-        };
-        {
-          const float4* src = kv2_ptr(0, 0);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) kv2r[i] = __ldg(src + i * 32);
-        }
-#pragma unroll
-        for (int T = 0; T < 2; ++T) {
-          if (T < nT) {
-            const float* my_q = &q_cur[T][quarter][hh * 64];
-            const float4* nxt = (T + 1 < nT) ? kv2_ptr(T + 1, 0) : kv2_ptr(0, 1);   // next user of the buffer
-            wait_acc(T);
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              float k[16];
-              tmem_ld16(lane_addr + (T ? ACC1 : ACC0) + hh * 64 + h * 16, k);
-              tmem_ld_wait();
-              float d1 = 0.f, d2 = 0.f;
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                const float4 qq = reinterpret_cast<const float4*>(my_q + h * 16)[q4];
-                d1 = fmaf(qq.x, k[4*q4], d1); d1 = fmaf(qq.y, k[4*q4+1], d1);
-                d1 = fmaf(qq.z, k[4*q4+2], d1); d1 = fmaf(qq.w, k[4*q4+3], d1);
-                const float4 kk = kv2r[h * 4 + q4];
-                d2 = fmaf(qq.x, kk.x, d2); d2 = fmaf(qq.y, kk.y, d2); d2 = fmaf(qq.z, kk.z, d2); d2 = fmaf(qq.w, kk.w, d2);
-              }
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) kv2r[h * 4 + q4] = __ldg(nxt + (h * 4 + q4) * 32);
-              d1 *= 0.25f;
-              d2 = has2 ? d2 * 0.25f : -3.4e38f;
-              const float mx = warp_max(fmaxf(d1, d2));
-              const float e1 = expf(d1 - mx), e2 = has2 ? expf(d2 - mx) : 0.f;
-              const float inv = 1.0f / warp_sum(e1 + e2);
-              w1[T][h] = e1 * inv;
-              w2[T][h] = e2 * inv;
-            }
-            free_acc(T);                                               // J6(T) may now overwrite the K logits
-          }
-        }
-#pragma unroll
-        for (int T = 0; T < 2; ++T) {
-          if (T < nT) {
-            float* my_attr = &attr[T][warp][0];
-            const float4* nxt = (T + 1 < nT) ? kv2_ptr(T + 1, 1) : nullptr;
-            wait_acc(T);
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              float v[16], p[16];
-              tmem_ld16(lane_addr + (T ? ACC1 : ACC0) + hh * 64 + h * 16, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int q4 = 0; q4 < 4; ++q4) {
-                float4 vv = kv2r[h * 4 + q4];
-                if (!has2) vv = make_float4(0.f, 0.f, 0.f, 0.f);
-                p[4*q4]     = fmaf(w1[T][h], v[4*q4],     w2[T][h] * vv.x);
-                p[4*q4 + 1] = fmaf(w1[T][h], v[4*q4 + 1], w2[T][h] * vv.y);
-                p[4*q4 + 2] = fmaf(w1[T][h], v[4*q4 + 2], w2[T][h] * vv.z);
-                p[4*q4 + 3] = fmaf(w1[T][h], v[4*q4 + 3], w2[T][h] * vv.w);
-              }
-              if (nxt != nullptr) {
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) kv2r[h * 4 + q4] = __ldg(nxt + (h * 4 + q4) * 32);
-              }
-              if (h == 3) free_acc(T);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) p[i] += __shfl_xor_sync(0xffffffffu, p[i], 16);
-#pragma unroll
-              for (int off = 8, n = 8; off >= 1; off >>= 1, n >>= 1) {
-                const bool upper = (lane & off) != 0;
-#pragma unroll
-                for (int i = 0; i < n; ++i) {
-                  const float send = upper ? p[i] : p[i + n];
-                  const float keep = upper ? p[i + n] : p[i];
-                  p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-              }
-              if (lane < 16) my_attr[h * 16 + lane] = p[0];
-            }
-            __syncwarp();
-            // operand of J7: att_r of this sentence / column half in the relay row of AX(T) (J5/J6 have completed)
-            uint32_t hi[32], lo[32];
-            split_half_row_smem(my_attr, hi, lo);
-            patch_relay_row(T, hi, lo);
-            x_done(T);
-            __syncwarp();
-          }
-        }
-
-        // ================= J7: s' = relu(att_r @ Wo_relay + b) on the relay lane -> relay row of AX(T) (operand of J8 and
-        // of the next cycle's QKV jobs)
-#pragma unroll
-        for (int T = 0; T < 2; ++T) {
-          if (T < nT) {
-            float* my_s = &s_cur[T][quarter][hh * 64];
-            wait_acc(T);
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              float v[32];
-              tmem_ld32(lane_addr + (T ? ACC1 : ACC0) + hh * 64 + j * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_r + hh * 64 + j * 32) + q4);
-                v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
-                v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
-                v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
-                v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
-              }
-              if (lane == 31) {
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4)
-                  reinterpret_cast<float4*>(my_s)[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-                if (last) {
-                  float4* xr = reinterpret_cast<float4*>(Xrow + ((int64_t)tile_of(T) * 128 + row_in_tile) * 128 + hh * 64);
-#pragma unroll
-                  for (int q4 = 0; q4 < 8; ++q4) xr[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-                }
-              }
-#pragma unroll
-              for (int q2 = 0; q2 < 16; ++q2) split2(v[2*q2], v[2*q2+1], hi[j * 16 + q2], lo[j * 16 + q2]);
-            }
-            free_acc(T);
-            if (!last) {
-              patch_relay_row(T, hi, lo);                              // J7 has completed (its accumulator was drained)
-              x_done(T);
-            }
-          }
-        }
-        if (!last) {
-          load_kve(0, 0, kv);                                          // e-keys of the next cycle's first head
-          // ================= J8: q' = s' @ Wq_relay on the relay lane
-#pragma unroll
-          for (int T = 0; T < 2; ++T) {
-            if (T < nT) {
-              float* my_q = &q_cur[T][quarter][hh * 64];
-              wait_acc(T);
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                float v[32];
-                tmem_ld32(lane_addr + (T ? ACC1 : ACC0) + hh * 64 + j * 32, v);
-                tmem_ld_wait();
-                if (lane == 31) {
-#pragma unroll
-                  for (int q4 = 0; q4 < 8; ++q4)
-                    reinterpret_cast<float4*>(my_q)[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-                }
-              }
-              free_acc(T);
-              __syncwarp();
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == sf2::kMmaWarp) tmem_dealloc<512>(tmem_base);
-}
-
 }  // namespace dsc
 
 using namespace dsc;
@@ -965,19 +478,12 @@ using namespace dsc;
 template <int NPASS>
 static int launch_star_fused(const float* xi0, const float* s0, const float* q0, const float* kvei, const float* kv2i, int n2,
                              const sf::Weights& w, const float* bias_o, const float* bias_r, float* xrow, int n_tiles,
-                             int n_cycles, int variant, cudaStream_t s) {
+                             int n_cycles, cudaStream_t s) {
   constexpr size_t smem = (size_t)sf::STAGES * sf::STAGE_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(star_fused_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("dsc_star_cycles_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
   const int grid = n_tiles < kSMs ? n_tiles : kSMs;
-  cudaError_t e;
-  if (variant == 1) {
-    e = cudaFuncSetAttribute(star_fused_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("dsc_star_cycles_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
-    star_fused_kernel<NPASS><<<grid, sf::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles);
-  } else {
-    e = cudaFuncSetAttribute(star_fused2_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("dsc_star_cycles_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
-    star_fused2_kernel<NPASS><<<grid, sf2::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles);
-  }
+  star_fused_kernel<NPASS><<<grid, sf::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles);
   return check_launch("dsc_star_cycles_tc");
 }
 
@@ -995,14 +501,12 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
               aligned16(bias_o) && aligned16(bias_o_relay) && aligned16(x_rowmajor), "dsc_star_cycles_tc: misaligned pointer");
   DSC_REQUIRE((((uintptr_t)packed_wqkv_grouped | (uintptr_t)packed_wo | (uintptr_t)packed_wkv_relay | (uintptr_t)packed_wo_relay |
                 (uintptr_t)packed_wq_relay) & 127u) == 0, "dsc_star_cycles_tc: packed weights must be 128-byte aligned");
-  const int variant = (prec >> 8) == 1 ? 1 : 2;   // bring-up knob: prec | 0x100 selects the one-tile-at-a-time kernel
-  prec &= 255;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_cycles_tc: prec must be 1 (bf16x3) or 2 (bf16)");
   if (n_sent == 0) return DSC_OK;
   if (n2 == 0) kv2 = kv_e;        // rows are read but masked (lane < n2 is false): any readable [n_sent][64][32][4] floats do
   sf::Weights w{reinterpret_cast<const uint8_t*>(packed_wqkv_grouped), reinterpret_cast<const uint8_t*>(packed_wo),
                 reinterpret_cast<const uint8_t*>(packed_wkv_relay), reinterpret_cast<const uint8_t*>(packed_wo_relay),
                 reinterpret_cast<const uint8_t*>(packed_wq_relay)};
-  return prec == 1 ? launch_star_fused<3>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, variant, as_stream(stream))
-                   : launch_star_fused<1>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, variant, as_stream(stream));
+  return prec == 1 ? launch_star_fused<3>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, as_stream(stream))
+                   : launch_star_fused<1>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, as_stream(stream));
 }
