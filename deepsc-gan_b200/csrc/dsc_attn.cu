@@ -184,6 +184,82 @@ mha_attention_kernel(const float* __restrict__ q, int64_t ldq, int64_t qbs,
   }
 }
 
+// ---------------------------------------------------------------- K5, single query (greedy decode step)
+// One warp per (sentence, head): lane = key (two keys per lane when lk > 32).  No shared-memory staging: each key /
+// value row slice (16 floats) is read once.  Same masking and arithmetic as mha_attention_kernel.
+__global__ void __launch_bounds__(256)
+mha_decode_attention_kernel(const float* __restrict__ q, int64_t qbs, const float* __restrict__ k, const float* __restrict__ v,
+                            int64_t ldkv, int64_t kvbs, float* __restrict__ out, int64_t obs,
+                            const float* __restrict__ mask, int64_t mbs,
+                            const int32_t* __restrict__ key_ids, int64_t kis, int causal, int q_off, int n, int lk) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gw >= n * 8) return;
+  const int b = gw >> 3, head = gw & 7;
+  float qh[16];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(q + (int64_t)b * qbs + head * 16);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { const float4 a = __ldg(qp + t); qh[4*t] = a.x; qh[4*t+1] = a.y; qh[4*t+2] = a.z; qh[4*t+3] = a.w; }
+  }
+  float lg[2], w[2];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int j = lane + 32 * half;
+    float d = -3.4e38f;
+    if (j < lk) {
+      const float4* kp = reinterpret_cast<const float4*>(k + (int64_t)b * kvbs + (int64_t)j * ldkv + head * 16);
+      d = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 a = __ldg(kp + t);
+        d = fmaf(qh[4*t], a.x, d); d = fmaf(qh[4*t+1], a.y, d); d = fmaf(qh[4*t+2], a.z, d); d = fmaf(qh[4*t+3], a.w, d);
+      }
+      d *= 0.25f;
+      float m = (key_ids != nullptr && key_ids[(int64_t)b * kis + j] == 0) ? 1.f : 0.f;
+      if (mask != nullptr) m = fmaxf(m, __ldg(mask + (int64_t)b * mbs + j));
+      if (causal && j > q_off) m = 1.f;
+      d += m * -1e9f;
+    }
+    lg[half] = d;
+  }
+  const float mx = warp_max(fmaxf(lg[0], lg[1]));
+  w[0] = (lane < lk) ? expf(lg[0] - mx) : 0.f;
+  w[1] = (lane + 32 < lk) ? expf(lg[1] - mx) : 0.f;
+  const float inv = 1.0f / warp_sum(w[0] + w[1]);
+  float p[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) p[t] = 0.f;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int j = lane + 32 * half;
+    if (j < lk) {
+      const float4* vp = reinterpret_cast<const float4*>(v + (int64_t)b * kvbs + (int64_t)j * ldkv + head * 16);
+      const float ww = w[half] * inv;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 a = __ldg(vp + t);
+        p[4*t] = fmaf(ww, a.x, p[4*t]); p[4*t+1] = fmaf(ww, a.y, p[4*t+1]);
+        p[4*t+2] = fmaf(ww, a.z, p[4*t+2]); p[4*t+3] = fmaf(ww, a.w, p[4*t+3]);
+      }
+    }
+  }
+  // sum over the 32 lanes: fold the half-warps, then reduce-scatter 16 values over 16 lanes (lane l ends with dim l & 15)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) p[i] += __shfl_xor_sync(0xffffffffu, p[i], 16);
+#pragma unroll
+  for (int off = 8, m = 8; off >= 1; off >>= 1, m >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      const float send = upper ? p[i] : p[i + m];
+      const float keep = upper ? p[i + m] : p[i];
+      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  if (lane < 16) out[(int64_t)b * obs + head * 16 + lane] = p[0];
+}
+
 }  // namespace dsc
 
 using namespace dsc;
@@ -218,6 +294,11 @@ extern "C" int dsc_mha_attention(const float* q, int64_t ldq, int64_t qbs, const
   DSC_REQUIRE(((ldq | qbs | ldkv | kvbs | ldo | obs) & 3) == 0 && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out),
               "dsc_mha_attention: rows must be 16-byte aligned");
   if (n == 0) return DSC_OK;
+  if (lq == 1) {                       // greedy decode step: one query per sentence, warp per (sentence, head)
+    mha_decode_attention_kernel<<<(n * 8 * 32 + 255) / 256, 256, 0, as_stream(stream)>>>(
+        q, qbs, k, v, ldkv, kvbs, out, obs, mask, mbs, key_ids, kis, causal, q_off, n, lk);
+    return check_launch("dsc_mha_attention");
+  }
   static bool attr_set = false;
   size_t smem = (size_t)lk * 128 * 2 * sizeof(float);
   if (!attr_set) {

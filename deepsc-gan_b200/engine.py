@@ -65,7 +65,7 @@ class _StarLayerState:
     def __init__(self, layer, relay, ln_a, ln_b, n_sent, max_len, device):
         f = dict(device=device, dtype=torch.float32)
         self.layer, self.relay, self.ln_a, self.ln_b = layer, relay, ln_a, ln_b
-        self.kv_tar = torch.empty((n_sent, max_len, 256), **f)   # k|v of tar rows under multi_tar
+        self.qkv_tar = torch.empty((n_sent, max_len, 384), **f)  # q|k|v of tar rows under multi_tar (one projection)
         self.kv2 = torch.empty((n_sent, max_len, 256), **f)      # k|v of h2 rows under the relay weights
         self.kv2i = torch.zeros((n_sent * 8192,), **f)           # same cache, interleaved (tcgen05 path)
         self.kv2_row = torch.empty((n_sent, 256), **f)
@@ -108,9 +108,9 @@ class StarGreedyDecoder:
             x2 = x_t.view(S, 128)
             for li, st in enumerate(self.layers):
                 L = st.layer
-                q_t = L.multi_tar.wq(x2).view(S, 1, 128)
-                _lib.linear(x2, L.multi_tar._packed("kv"), None, out=st.kv_tar[:, t, :], prec=M.PREC)
-                a = L.multi_tar.attend(q_t, st.kv_tar[:, :t + 1, 0:128], st.kv_tar[:, :t + 1, 128:256],
+                _lib.linear(x2, L.multi_tar._packed("qkv"), None, out=st.qkv_tar[:, t, :], prec=M.PREC)
+                a = L.multi_tar.attend(st.qkv_tar[:, t:t + 1, 0:128], st.qkv_tar[:, :t + 1, 128:256],
+                                       st.qkv_tar[:, :t + 1, 256:384],
                                        key_ids=self.outputs)           # causal: the newest row sees the whole prefix
                 h2_t = _add_ln(a, x_t, L.layernorm1)
                 if tc:
@@ -140,7 +140,7 @@ class BaselineGreedyDecoder:
         dev = dec.embedding.embeddings.device
         f = dict(device=dev, dtype=torch.float32)
         self.net, self.dec, self.n, self.max_length = net, dec, n_sent, max_length
-        self.kv_self = [torch.empty((n_sent, max_length, 256), **f) for _ in dec.dec_layers]
+        self.qkv_self = [torch.empty((n_sent, max_length, 384), **f) for _ in dec.dec_layers]
         self.kv_cross = [torch.empty((n_sent, 31, 256), **f) for _ in dec.dec_layers]
         self.outputs = torch.zeros((n_sent, max_length + 1), device=dev, dtype=torch.int32)
         self.vocab = dec.final_layer.kernel.shape[1]
@@ -156,11 +156,11 @@ class BaselineGreedyDecoder:
         wf, bf = dec.final_layer.padded_kernel(), dec.final_layer.bias.detach()
         for t in range(self.max_length):
             x = dec._embed(self.outputs[:, t:t + 1], pos0=t)          # [S,1,128]
-            for L, kvs, kvc in zip(dec.dec_layers, self.kv_self, self.kv_cross):
+            for L, kvs, kvc in zip(dec.dec_layers, self.qkv_self, self.kv_cross):
                 x2 = x.view(S, 128)
-                q = L.sl11.wq(x2).view(S, 1, 128)
-                _lib.linear(x2, L.sl11._packed("kv"), None, out=kvs[:, t, :], prec=M.PREC)
-                a = L.sl11.attend(q, kvs[:, :t + 1, 0:128], kvs[:, :t + 1, 128:256], key_ids=self.outputs)
+                _lib.linear(x2, L.sl11._packed("qkv"), None, out=kvs[:, t, :], prec=M.PREC)
+                a = L.sl11.attend(kvs[:, t:t + 1, 0:128], kvs[:, :t + 1, 128:256], kvs[:, :t + 1, 256:384],
+                                  key_ids=self.outputs)
                 o1 = _add_ln(a, x, L.layernorm1)
                 q2 = L.sl12.wq(o1.view(S, 128)).view(S, 1, 128)
                 a2 = L.sl12.attend(q2, kvc[:, :, 0:128], kvc[:, :, 128:256], key_ids=inp)

@@ -488,3 +488,30 @@ def test_baseline_train_step_and_gan_train_step(dev):
         n_big += int(ok.sum())
         n_bad += int((((prm.detach().cpu() - ref) - (val - ref)).abs()[ok] > 0.05 * 5e-4).sum())
     assert n_big > 100000 and n_bad <= 2e-3 * n_big, (n_bad, n_big)
+
+
+def test_training_with_dropout_and_attack_step_run(dev):
+    """training=True applies dropout at the reference's sites (star layers use their constructor default 0.1): the loss
+    changes with the dropout seed, stays finite, and train_attack_step (FGM adversarial training, utlis/trainer.py:30-64)
+    runs end to end and moves the parameters."""
+    import deepsc_gan_b200.models.modules as Mod
+    from deepsc_gan_b200.utlis import trainer as T
+    args, net = build("Transeiver_Star", dev)
+    inp = _cases.synthetic_unit(6).to(dev)
+    z, z2 = _cases.draws()[0].to(dev), _cases.draws()[1].to(dev)
+    n_std = O.snr_to_noise(3.0)
+    losses = []
+    for seed in (1, 2):
+        Mod.set_dropout_seed(seed)
+        with Mod.differentiable(), torch.no_grad():
+            m = Mod.create_masks(inp, inp[:, :-1])
+            outs = net(inp, inp[:, :-1], None, 0, channel="AWGN", n_std=n_std, training=True, enc_padding_mask=m[0],
+                       combined_mask=m[1], dec_padding_mask=m[2], noise=z)
+            losses.append(float(Mod.loss_function(inp, outs[0])))
+    assert all(math.isfinite(v) for v in losses) and abs(losses[0] - losses[1]) > 1e-6
+    opt = T.make_optimizer(net)
+    before = opt.fp.flat.clone()
+    loss, loss_m = T.train_attack_step(inp, inp, None, 3.0, net, opt, channel="AWGN", n_std=n_std, noise=z, noise2=z2)
+    assert math.isfinite(float(loss)) and math.isfinite(float(loss_m)) and opt.iterations == 1
+    moved = (opt.fp.flat - before).abs()
+    assert float(moved.max()) > 1e-5 and float(moved.max()) < 1e-3            # one Adam step of lr 5e-4
