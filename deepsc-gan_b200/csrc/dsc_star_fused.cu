@@ -23,8 +23,9 @@
 // kernel is bound by the latency of the register-side work (tcgen05.ld -> shuffles -> tcgen05.st chains at 2 warps per
 // scheduler), not by UMMA latency, and the extra live state spilled.  The next step is more compute warps per tile.
 //
-// Warps: 0-7 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, hh = warp >> 2 the column half),
-// 8 = UMMA issuer, 9 = weight producer.  Arithmetic as in dsc_star_tc.cu: prec 1 = bf16x3, 2 = bf16; fp32 softmax.
+// Warps: 0-15 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, sub = warp >> 2 the column quarter),
+// 16 = UMMA issuer, 17 = weight producer.  The register-side work is latency-bound (tcgen05.ld -> shuffles ->
+// tcgen05.st chains), so it is spread over 4 warps per scheduler: every warp owns 32 of the 128 columns of a row.  Arithmetic as in dsc_star_tc.cu: prec 1 = bf16x3, 2 = bf16; fp32 softmax.
 #include "dsc_star_common.cuh"
 
 namespace dsc {
@@ -32,7 +33,7 @@ namespace dsc {
 using namespace tc;
 
 namespace sf {
-constexpr int kCompute = 8, kMmaWarp = 8, kProdWarp = 9, kThreads = 320;
+constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = 576;
 constexpr int STAGES = 3;
 constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
@@ -71,6 +72,30 @@ __device__ __forceinline__ void split_half_row_smem(const float* p, uint32_t* hi
   }
 }
 
+// 32 fp32 values -> 16 hi + 16 lo packed bf16 words; src = element (k4 = 0, this row), consecutive k4 `stride4` float4 apart
+__device__ __forceinline__ void load_quarter_row(const float4* __restrict__ src, int stride4, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = __ldg(src + (int64_t)q * stride4);
+    split2(v.x, v.y, hi[2 * q], lo[2 * q]);
+    split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
+  }
+}
+__device__ __forceinline__ void split_quarter_row(const float* v, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int q2 = 0; q2 < 16; ++q2) split2(v[2 * q2], v[2 * q2 + 1], hi[q2], lo[q2]);
+}
+// operand columns of k = 32*sub .. 32*sub+31: 16 hi columns and 16 lo columns
+template <int NPASS>
+__device__ __forceinline__ void store_quarter_row(uint32_t lane_addr, uint32_t a_hi, uint32_t a_lo, int sub,
+                                                  const uint32_t* hi, const uint32_t* lo) {
+  tmem_st16(lane_addr + a_hi + sub * 16, hi);
+  if (NPASS == 3) tmem_st16(lane_addr + a_lo + sub * 16, lo);
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(n) : "memory");
+}
+
 template <int NPASS>
 __global__ void __launch_bounds__(sf::kThreads, 1)
 star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, const float* __restrict__ Q0,
@@ -84,15 +109,16 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_cur[4][128];      // relay node of the 4 sentences of the tile
   __shared__ __align__(16) float q_cur[4][128];      // its query under the relay weights
-  __shared__ __align__(16) float attr[8][64];        // per compute warp: relay attention output (its column half)
+  __shared__ __align__(16) float attr[4][128];       // relay attention output
   constexpr int parts = (NPASS == 3) ? 2 : 1;
+  constexpr uint32_t kComputeThreads = kCompute * 32;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_free[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kCompute * 32); }
-    mbar_init(&bars.x_ready, kCompute * 32);
-    mbar_init(&bars.t_ready, kCompute * 32);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kComputeThreads); }
+    mbar_init(&bars.x_ready, kComputeThreads);
+    mbar_init(&bars.t_ready, kComputeThreads);
     fence_barrier_init();
   }
   if (warp == sf::kMmaWarp) tmem_alloc<512>(&tmem_base_s);
@@ -151,16 +177,20 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ compute warps
-    const int quarter = warp & 3, hh = warp >> 2;
+    // ------------------------------------------------------------------ compute warps (16)
+    // quarter = TMEM lane quarter = sentence of the tile; sub = column quarter (32 of the 128 columns, = heads 2*sub,
+    // 2*sub+1 of the relay attention).  In the QKV phase sub also picks the accumulator: warps with sub < 2 take the
+    // even head pairs (ACC0), the others the odd ones (ACC1), head 2g + (sub & 1) each.
+    const int quarter = warp & 3, sub = warp >> 2;
+    const int gp = sub >> 1, hh = sub & 1;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int row_in_tile = quarter * 32 + lane;
     const int up = (lane >= 30) ? 0 : lane + 1;                    // roll(h,-1)[i] = h[(i+1) mod 31]
     const int dn = (lane == 0) ? 30 : lane - 1;                    // roll(h,+1)[i] = h[(i-1) mod 31]
-    float* my_s = &s_cur[quarter][hh * 64];
-    float* my_q = &q_cur[quarter][hh * 64];
-    float* my_attr = &attr[warp][0];
-    uint32_t use0 = 0, use1 = 0;                                   // accumulator phases consumed (scalars: no local memory)
+    float* my_s = &s_cur[quarter][sub * 32];
+    float* my_q = &q_cur[quarter][sub * 32];
+    float* my_attr = &attr[quarter][sub * 32];
+    uint32_t use0 = 0, use1 = 0;                                   // accumulator phases seen (scalars: no local memory)
     auto wait_acc = [&](int b) {
       if (b) { mbar_wait(&bars.acc_full[1], use1 & 1); ++use1; } else { mbar_wait(&bars.acc_full[0], use0 & 1); ++use0; }
       tc_fence_after();
@@ -171,42 +201,42 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
       const int t = blockIdx.x + ti * gridDim.x;
       const int64_t sent = (int64_t)t * 4 + quarter;
       const uint4* kve_base = reinterpret_cast<const uint4*>(KVEI + (int64_t)t * 32768) + row_in_tile;
-      uint32_t kv[32], kvn[32];                                    // e-keys k[16] | v[16] of (row, head): current, next
-      auto load_kve = [&](int g, uint32_t* dst) {
+      uint32_t kv[32];                                             // e-keys k[16] | v[16] of (row, head) as raw fp32 bits
+      auto load_kve = [&](int g) {
         const int head = 2 * g + hh;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint4 a = __ldg(kve_base + (head * 4 + q) * 128), c = __ldg(kve_base + (32 + head * 4 + q) * 128);
-          dst[4*q] = a.x; dst[4*q+1] = a.y; dst[4*q+2] = a.z; dst[4*q+3] = a.w;
-          dst[16+4*q] = c.x; dst[16+4*q+1] = c.y; dst[16+4*q+2] = c.z; dst[16+4*q+3] = c.w;
+          kv[4*q] = a.x; kv[4*q+1] = a.y; kv[4*q+2] = a.z; kv[4*q+3] = a.w;
+          kv[16+4*q] = c.x; kv[16+4*q+1] = c.y; kv[16+4*q+2] = c.z; kv[16+4*q+3] = c.w;
         }
       };
       // ---- tile start: relay vectors to shared memory, X rows to tensor memory (all UMMAs of the previous tile are
       //      complete: their last accumulator was drained below)
       {
-        const float4* s0 = reinterpret_cast<const float4*>(S0 + sent * 128 + hh * 64);
-        const float4* q0 = reinterpret_cast<const float4*>(Q0 + sent * 128 + hh * 64);
-        if (lane < 16) reinterpret_cast<float4*>(my_s)[lane] = __ldg(s0 + lane);
-        else reinterpret_cast<float4*>(my_q)[lane - 16] = __ldg(q0 + (lane - 16));
+        const float4* s0 = reinterpret_cast<const float4*>(S0 + sent * 128 + sub * 32);
+        const float4* q0 = reinterpret_cast<const float4*>(Q0 + sent * 128 + sub * 32);
+        if (lane < 8) reinterpret_cast<float4*>(my_s)[lane] = __ldg(s0 + lane);
+        else if (lane < 16) reinterpret_cast<float4*>(my_q)[lane - 8] = __ldg(q0 + (lane - 8));
         __syncwarp();
-        uint32_t hi[32], lo[32];
-        if (lane == 31) split_half_row_smem(my_s, hi, lo);
-        else load_half_row(reinterpret_cast<const float4*>(XI0 + (int64_t)t * 16384) + (hh * 16) * 128 + row_in_tile, 128, hi, lo);
-        store_half_row<NPASS>(lane_addr, AX_HI, AX_LO, hh, hi, lo);
+        uint32_t hi[16], lo[16];
+        if (lane == 31) split_quarter_row(my_s, hi, lo);
+        else load_quarter_row(reinterpret_cast<const float4*>(XI0 + (int64_t)t * 16384) + (sub * 8) * 128 + row_in_tile, 128, hi, lo);
+        store_quarter_row<NPASS>(lane_addr, AX_HI, AX_LO, sub, hi, lo);
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bars.x_ready);
       }
-      load_kve(0, kv);
+      load_kve(gp);
 
       for (int c = 0; c < n_cycles; ++c) {
         const bool last = (c + 1 == n_cycles);
-        // ================= J0..J3: satellite attention of head 2g + hh, output staged as the ATT operand
+        // ================= J0..J3: this warp takes head pairs g = gp and gp + 2 (accumulator gp), head 2g + hh
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int b = g & 1, head = 2 * g + hh;
-          if (g < 3) load_kve(g + 1, kvn);                          // e-keys of the next head: in flight during this one
-          wait_acc(b);
-          const uint32_t col = lane_addr + (b ? ACC1 : ACC0) + hh * 16;
+        for (int gi = 0; gi < 2; ++gi) {
+          const int g = gp + 2 * gi, head = 2 * g + hh;
+          wait_acc(gp);
+          const uint32_t col = lane_addr + (gp ? ACC1 : ACC0) + hh * 16;
           float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
           {
             float q[16], k[16];
@@ -233,7 +263,8 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           const float inv = 1.0f / (l0 + l1 + l2 + l3 + l4);
           l0 *= inv; l1 *= inv; l2 *= inv; l3 *= inv; l4 *= inv;
           tmem_ld_wait();
-          free_acc(b);
+          tc_fence_before();
+          mbar_arrive_n(&bars.acc_free[gp], 2);                     // 8 of the 16 warps drain a QKV accumulator
           uint32_t ohi[8], olo[8];
 #pragma unroll
           for (int d2 = 0; d2 < 8; ++d2) {
@@ -256,70 +287,65 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           // head `head` covers k = 16*head .. 16*head+15 = operand columns 8*head .. 8*head+7
           tmem_st8(lane_addr + AT_HI + head * 8, ohi);
           if (NPASS == 3) tmem_st8(lane_addr + AT_LO + head * 8, olo);
-          if (g < 3) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) kv[i] = kvn[i];
-          }
+          if (gi == 0) load_kve(g + 2);                             // e-keys of this warp's second head pair
         }
+        if (gp) use0 += 2; else use1 += 2;                          // the two QKV jobs drained by the other warps
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bars.t_ready);
 
-        // ================= J4: X' = relu(ATT @ Wo + b); the relay row keeps s; re-staged as the X operand
+        // ================= J4: X' = relu(ATT @ Wo + b), columns 32*sub..; the relay row keeps s; re-staged as X
         {
           wait_acc(0);
-          float4* xr = last ? reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + hh * 64) : nullptr;
-          uint32_t hi[32], lo[32];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            float v[32];
-            tmem_ld32(lane_addr + ACC0 + hh * 64 + j * 32, v);
-            tmem_ld_wait();
-            if (lane == 31) {
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 s4 = reinterpret_cast<const float4*>(my_s)[j * 8 + q4];
-                v[4*q4] = s4.x; v[4*q4+1] = s4.y; v[4*q4+2] = s4.z; v[4*q4+3] = s4.w;
-              }
-            } else {
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_o + hh * 64 + j * 32) + q4);
-                v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
-                v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
-                v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
-                v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
-              }
-            }
-            if (xr != nullptr) {
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) xr[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-            }
-#pragma unroll
-            for (int q2 = 0; q2 < 16; ++q2) split2(v[2*q2], v[2*q2+1], hi[j * 16 + q2], lo[j * 16 + q2]);
-          }
+          float v[32];
+          tmem_ld32(lane_addr + ACC0 + sub * 32, v);
+          tmem_ld_wait();
           free_acc(0);
-          store_half_row<NPASS>(lane_addr, AX_HI, AX_LO, hh, hi, lo);   // J0..J3 have completed (their commit precedes J4's)
+          if (lane == 31) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 s4 = reinterpret_cast<const float4*>(my_s)[q4];
+              v[4*q4] = s4.x; v[4*q4+1] = s4.y; v[4*q4+2] = s4.z; v[4*q4+3] = s4.w;
+            }
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_o + sub * 32) + q4);
+              v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
+              v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
+              v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
+              v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
+            }
+          }
+          if (last) {
+            float4* xr = reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + sub * 32);
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) xr[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+          }
+          uint32_t hi[16], lo[16];
+          split_quarter_row(v, hi, lo);
+          store_quarter_row<NPASS>(lane_addr, AX_HI, AX_LO, sub, hi, lo);   // J0..J3 have completed (their commit precedes J4's)
+          tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars.x_ready);
         }
 
-        // ================= J5 (K -> ACC1), J6 (V -> ACC0): relay attention, 4 heads per warp, lane = key row
+        // ================= J5 (K -> ACC1), J6 (V -> ACC0): relay attention, heads 2*sub and 2*sub+1, lane = key row
         {
-          const float4* kv2 = reinterpret_cast<const float4*>(KV2I + sent * 8192) + (hh * 16) * 32 + lane;
+          // h2 keys / values of this lane's row: KV2I [sentence][64 k4][32 rows][4]; k columns are k4 0..31, v 32..63.
+          // Row `lane` < 32 is always inside KV2I; rows >= n2 are masked in the arithmetic (unconditional loads keep the
+          // arrays in registers).
+          const float4* kv2 = reinterpret_cast<const float4*>(KV2I + sent * 8192) + (sub * 8) * 32 + lane;
           const bool has2 = lane < n2;
-          // the h2 keys / values of this lane's row are fetched (L2) before the accumulators are waited for: 16 + 16 float4
-          // (unconditional: row `lane` < 32 is always inside KV2I; rows >= n2 are masked in the arithmetic below.  A load
-          // under `if (has2)` makes the arrays conditionally defined and the compiler parks them in local memory.)
-          float4 k2[16], v2[16];
+          float4 k2[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) k2[i] = __ldg(kv2 + i * 32);
-          float w1[4], w2[4];
+          for (int i = 0; i < 8; ++i) k2[i] = __ldg(kv2 + i * 32);
+          float w1[2], w2[2];
           wait_acc(1);
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < 2; ++h) {
             float k[16];
-            tmem_ld16(lane_addr + ACC1 + hh * 64 + h * 16, k);
+            tmem_ld16(lane_addr + ACC1 + sub * 32 + h * 16, k);
             tmem_ld_wait();
             float d1 = 0.f, d2 = 0.f;
 #pragma unroll
@@ -339,24 +365,24 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             w2[h] = e2 * inv;
           }
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v2[i] = __ldg(kv2 + (32 + i) * 32);     // k2 is dead: its registers take the values
+          for (int i = 0; i < 8; ++i) k2[i] = __ldg(kv2 + (32 + i) * 32);      // the values take the keys' registers
           free_acc(1);
           wait_acc(0);
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < 2; ++h) {
             float v[16], p[16];
-            tmem_ld16(lane_addr + ACC0 + hh * 64 + h * 16, v);
+            tmem_ld16(lane_addr + ACC0 + sub * 32 + h * 16, v);
             tmem_ld_wait();
+            if (h == 1) free_acc(0);
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
-              float4 vv = v2[h * 4 + q4];
+              float4 vv = k2[h * 4 + q4];
               if (!has2) vv = make_float4(0.f, 0.f, 0.f, 0.f);                // masked rows may hold anything
               p[4*q4]     = fmaf(w1[h], v[4*q4],     w2[h] * vv.x);
               p[4*q4 + 1] = fmaf(w1[h], v[4*q4 + 1], w2[h] * vv.y);
               p[4*q4 + 2] = fmaf(w1[h], v[4*q4 + 2], w2[h] * vv.z);
               p[4*q4 + 3] = fmaf(w1[h], v[4*q4 + 3], w2[h] * vv.w);
             }
-            if (h == 3) free_acc(0);
             // sum over the 32 key lanes: fold the half-warps, then reduce-scatter 16 values over 16 lanes;
             // lane l (and l ^ 16) ends with dimension l & 15 of this head
 #pragma unroll
@@ -374,91 +400,92 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             if (lane < 16) my_attr[h * 16 + lane] = p[0];
           }
           __syncwarp();
-          // att_r of this sentence / column half as the operand of J7: every lane stages the same 64 values (only the
+          // att_r of this sentence / column quarter as the operand of J7: every lane stages the same 32 values (only the
           // relay lane's row of the product is used)
-          uint32_t hi[32], lo[32];
-          split_half_row_smem(my_attr, hi, lo);
-          store_half_row<NPASS>(lane_addr, AT_HI, AT_LO, hh, hi, lo);   // J4 (the last reader of ATT) has completed
+          uint32_t hi[16], lo[16];
+          {
+            float a[32];
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 t4 = reinterpret_cast<const float4*>(my_attr)[q4];
+              a[4*q4] = t4.x; a[4*q4+1] = t4.y; a[4*q4+2] = t4.z; a[4*q4+3] = t4.w;
+            }
+            split_quarter_row(a, hi, lo);
+          }
+          store_quarter_row<NPASS>(lane_addr, AT_HI, AT_LO, sub, hi, lo);     // J4 (the last reader of ATT) has completed
+          tmem_st_wait();
           tc_fence_before();
           mbar_arrive(&bars.t_ready);
           __syncwarp();
         }
 
-        // ================= J7: s' = relu(att_r @ Wo_relay + b) on the relay lane; operand of J8; relay row of X patched
+        // ================= J7 (ACC0): s' = relu(att_r @ Wo_relay + b) on the relay lane; operand of J8; relay row of X patched
         {
           wait_acc(0);
-          uint32_t hi[32], lo[32];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            float v[32];
-            tmem_ld32(lane_addr + ACC0 + hh * 64 + j * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_r + hh * 64 + j * 32) + q4);
-              v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
-              v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
-              v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
-              v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
-            }
-            if (lane == 31) {
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4)
-                reinterpret_cast<float4*>(my_s)[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-              if (last) {
-                float4* xr = reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + hh * 64);
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) xr[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-              }
-            }
-#pragma unroll
-            for (int q2 = 0; q2 < 16; ++q2) split2(v[2*q2], v[2*q2+1], hi[j * 16 + q2], lo[j * 16 + q2]);
-          }
+          float v[32];
+          tmem_ld32(lane_addr + ACC0 + sub * 32, v);
+          tmem_ld_wait();
           free_acc(0);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_r + sub * 32) + q4);
+            v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
+            v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
+            v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
+            v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
+          }
+          if (lane == 31) {
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4)
+              reinterpret_cast<float4*>(my_s)[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+            if (last) {
+              float4* xr = reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + sub * 32);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) xr[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+            }
+          }
           if (!last) {
-            store_half_row<NPASS>(lane_addr, AT_HI, AT_LO, hh, hi, lo);      // operand of J8 (J7 has completed)
+            uint32_t hi[16], lo[16];
+            split_quarter_row(v, hi, lo);
+            store_quarter_row<NPASS>(lane_addr, AT_HI, AT_LO, sub, hi, lo);  // operand of J8 (J7 has completed)
+            tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars.t_ready);
             // patch the relay row of the X operand with s' (J5/J6, the last readers of X', have completed): every lane
             // rewrites its own row unchanged, the relay lane substitutes the new words
-#pragma unroll
-            for (int c4 = 0; c4 < 2; ++c4) {
+            {
               uint32_t w[16];
-              tmem_ld16(lane_addr + AX_HI + hh * 32 + c4 * 16, reinterpret_cast<float*>(w));
+              tmem_ld16(lane_addr + AX_HI + sub * 16, reinterpret_cast<float*>(w));
               tmem_ld_wait();
               if (lane == 31) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) w[i] = hi[c4 * 16 + i];
+                for (int i = 0; i < 16; ++i) w[i] = hi[i];
               }
-              tmem_st16(lane_addr + AX_HI + hh * 32 + c4 * 16, w);
+              tmem_st16(lane_addr + AX_HI + sub * 16, w);
               if (NPASS == 3) {
-                tmem_ld16(lane_addr + AX_LO + hh * 32 + c4 * 16, reinterpret_cast<float*>(w));
+                tmem_ld16(lane_addr + AX_LO + sub * 16, reinterpret_cast<float*>(w));
                 tmem_ld_wait();
                 if (lane == 31) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) w[i] = lo[c4 * 16 + i];
+                  for (int i = 0; i < 16; ++i) w[i] = lo[i];
                 }
-                tmem_st16(lane_addr + AX_LO + hh * 32 + c4 * 16, w);
+                tmem_st16(lane_addr + AX_LO + sub * 16, w);
               }
             }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars.x_ready);
-            load_kve(0, kv);                                             // e-keys of the next cycle's first head
-            // ================= J8: q' = s' @ Wq_relay on the relay lane
+            load_kve(gp);                                                // e-keys of the next cycle's first head pair
+            // ================= J8 (ACC1): q' = s' @ Wq_relay on the relay lane
             wait_acc(1);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              float v[32];
-              tmem_ld32(lane_addr + ACC1 + hh * 64 + j * 32, v);
-              tmem_ld_wait();
-              if (lane == 31) {
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4)
-                  reinterpret_cast<float4*>(my_q)[j * 8 + q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-              }
-            }
+            tmem_ld32(lane_addr + ACC1 + sub * 32, v);
+            tmem_ld_wait();
             free_acc(1);
+            if (lane == 31) {
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4)
+                reinterpret_cast<float4*>(my_q)[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+            }
             __syncwarp();
           }
         }
@@ -469,7 +496,6 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
   __syncthreads();
   if (warp == sf::kMmaWarp) tmem_dealloc<512>(tmem_base);
 }
-
 
 }  // namespace dsc
 
