@@ -95,3 +95,31 @@ def test_flat_params_views_and_ranges():
     assert len(r) == 1 and r[0][1] == fp.numel
     fp.flat.zero_()
     assert all(float(p.abs().sum()) == 0 for p in lin.parameters())
+
+
+def test_dataloader_mirror(tmp_path):
+    """dataset/dataloader.py: post-padding to 31, pre-truncation, (x, x) pairs, batch 64 with a short last batch,
+    a fresh permutation per epoch, raw_data[:-1] (the reference's length=-1 slice)."""
+    import pickle
+    from types import SimpleNamespace
+    from deepsc_gan_b200.dataset import dataloader as D
+    rng = np.random.RandomState(0)
+    raw = [[1] + rng.randint(5, 22234, size=n).tolist() + [4, 2] for n in rng.randint(4, 29, size=150)]
+    raw.append(list(range(1, 41)))                                   # longer than 31: truncated from the front
+    raw.append([1, 9, 2])                                            # dropped by raw_data[:-1]
+    path = tmp_path / "data.pkl"
+    pickle.dump(raw, open(path, "wb"))
+    pad = D.pad_sequences(raw[:-1])
+    assert pad.shape == (151, 31) and pad.dtype == np.int32
+    assert pad[0, : len(raw[0])].tolist() == raw[0] and not pad[0, len(raw[0]):].any()
+    assert pad[150].tolist() == list(range(10, 41))
+    ds = D.return_dataset(SimpleNamespace(bs=64), str(path), -1, seed=3)
+    assert len(ds) == 3
+    e1 = [b for b in ds]
+    e2 = [b for b in ds]
+    assert [tuple(x.shape) for x, _ in e1] == [(64, 31), (64, 31), (23, 31)]
+    assert all(torch.equal(x, y) for x, y in e1)
+    seen = torch.cat([x for x, _ in e1])
+    assert sorted(map(tuple, seen.tolist())) == sorted(map(tuple, pad.tolist()))
+    assert not torch.equal(seen, torch.cat([x for x, _ in e2]))      # reshuffled each epoch
+    assert tuple(ds.as_units().shape) == (128, 31)
