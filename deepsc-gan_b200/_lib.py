@@ -105,7 +105,7 @@ class _timed:
     """with _timed("dsc_x", meta): launch  -> PROFILE.append(("dsc_x", ev0, ev1, meta)) when profiling is on."""
 
     def __init__(self, op: str, meta):
-        self.on = PROFILE is not None and op in PROFILE_OPS
+        self.on = PROFILE is not None and op in PROFILE_OPS and not torch.cuda.is_current_stream_capturing()
         self.op, self.meta = op, meta
 
     def __enter__(self):

@@ -111,14 +111,14 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
   __shared__ __align__(16) float q_cur[4][128];      // its query under the relay weights
   __shared__ __align__(16) float attr[4][128];       // relay attention output
   constexpr int parts = (NPASS == 3) ? 2 : 1;
-  constexpr uint32_t kComputeThreads = kCompute * 32;
+  constexpr uint32_t kArrivals = kCompute;            // one elected arrival per compute warp (after __syncwarp)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_free[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kComputeThreads); }
-    mbar_init(&bars.x_ready, kComputeThreads);
-    mbar_init(&bars.t_ready, kComputeThreads);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kArrivals); }
+    mbar_init(&bars.x_ready, kArrivals);
+    mbar_init(&bars.t_ready, kArrivals);
     fence_barrier_init();
   }
   if (warp == sf::kMmaWarp) tmem_alloc<512>(&tmem_base_s);
@@ -195,7 +195,13 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
       if (b) { mbar_wait(&bars.acc_full[1], use1 & 1); ++use1; } else { mbar_wait(&bars.acc_full[0], use0 & 1); ++use0; }
       tc_fence_after();
     };
-    auto free_acc = [&](int b) { tc_fence_before(); mbar_arrive(&bars.acc_free[b]); };
+    // every lane fences its own TMEM accesses, the warp converges, one lane arrives for the warp
+    auto warp_arrive = [&](uint64_t* bar, uint32_t n) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_n(bar, n);
+    };
+    auto free_acc = [&](int b) { warp_arrive(&bars.acc_free[b], 1); };
 
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int t = blockIdx.x + ti * gridDim.x;
@@ -224,8 +230,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
         else load_quarter_row(reinterpret_cast<const float4*>(XI0 + (int64_t)t * 16384) + (sub * 8) * 128 + row_in_tile, 128, hi, lo);
         store_quarter_row<NPASS>(lane_addr, AX_HI, AX_LO, sub, hi, lo);
         tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars.x_ready);
+        warp_arrive(&bars.x_ready, 1);
       }
       load_kve(gp);
 
@@ -263,8 +268,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           const float inv = 1.0f / (l0 + l1 + l2 + l3 + l4);
           l0 *= inv; l1 *= inv; l2 *= inv; l3 *= inv; l4 *= inv;
           tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive_n(&bars.acc_free[gp], 2);                     // 8 of the 16 warps drain a QKV accumulator
+          warp_arrive(&bars.acc_free[gp], 2);                       // 8 of the 16 warps drain a QKV accumulator
           uint32_t ohi[8], olo[8];
 #pragma unroll
           for (int d2 = 0; d2 < 8; ++d2) {
@@ -291,8 +295,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
         }
         if (gp) use0 += 2; else use1 += 2;                          // the two QKV jobs drained by the other warps
         tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&bars.t_ready);
+        warp_arrive(&bars.t_ready, 1);
 
         // ================= J4: X' = relu(ATT @ Wo + b), columns 32*sub..; the relay row keeps s; re-staged as X
         {
@@ -326,8 +329,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           split_quarter_row(v, hi, lo);
           store_quarter_row<NPASS>(lane_addr, AX_HI, AX_LO, sub, hi, lo);   // J0..J3 have completed (their commit precedes J4's)
           tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&bars.x_ready);
+          warp_arrive(&bars.x_ready, 1);
         }
 
         // ================= J5 (K -> ACC1), J6 (V -> ACC0): relay attention, heads 2*sub and 2*sub+1, lane = key row
@@ -414,8 +416,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           }
           store_quarter_row<NPASS>(lane_addr, AT_HI, AT_LO, sub, hi, lo);     // J4 (the last reader of ATT) has completed
           tmem_st_wait();
-          tc_fence_before();
-          mbar_arrive(&bars.t_ready);
+          warp_arrive(&bars.t_ready, 1);
           __syncwarp();
         }
 
@@ -449,8 +450,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             split_quarter_row(v, hi, lo);
             store_quarter_row<NPASS>(lane_addr, AT_HI, AT_LO, sub, hi, lo);  // operand of J8 (J7 has completed)
             tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars.t_ready);
+            warp_arrive(&bars.t_ready, 1);
             // patch the relay row of the X operand with s' (J5/J6, the last readers of X', have completed): every lane
             // rewrites its own row unchanged, the relay lane substitutes the new words
             {
@@ -473,8 +473,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
               }
             }
             tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars.x_ready);
+            warp_arrive(&bars.x_ready, 1);
             load_kve(gp);                                                // e-keys of the next cycle's first head pair
             // ================= J8 (ACC1): q' = s' @ Wq_relay on the relay lane
             wait_acc(1);

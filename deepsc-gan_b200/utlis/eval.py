@@ -201,7 +201,7 @@ def _attacked_greedy(args, inp, net, PNR_dB, channel, n_std, pertutation, noise,
                            seed=seed, h=_fading_h(channel, h, dev), p=pertutation if channel == 'AWGN' else None,
                            p_scale=ps if channel == 'AWGN' else None, want_x_norm=True)
     if decoder is None:
-        decoder = engine.make_decoder(net, inp32.shape[0], args.max_length)
+        decoder = engine.make_decoder(net, inp32.shape[0], args.max_length, graph=False)
     if isinstance(decoder, engine.StarGreedyDecoder):
         outputs = decoder.decode(y, args.start_idx)
     else:

@@ -172,3 +172,24 @@ def test_training_mode_raises(dev):
     inp = _cases.synthetic_unit(0).to(dev)
     with pytest.raises(RuntimeError, match="differentiable"):      # dropout + backward live in the differentiable mode
         net.semantic_encoder.call(inp, True, None)
+
+
+@pytest.mark.parametrize("kind", ["Transeiver", "Transeiver_Star"])
+def test_graph_replay_decoder_equals_eager(dev, kind):
+    """engine.GraphedDecoder (one CUDA-graph launch per batch) returns the ids of the eager loop, also on replay with
+    new inputs."""
+    from deepsc_gan_b200 import engine
+    args, net = build(kind, dev)
+    n_std = torch.full((2,), float(O.snr_to_noise(6.0)), device=dev)
+    eager = engine.make_decoder(net, 128, graph=False)
+    graphed = engine.make_decoder(net, 128, graph=True)
+    assert isinstance(graphed, engine.GraphedDecoder)
+    g = torch.Generator().manual_seed(5)
+    for first in (0, 2, 4):
+        inp = _cases.synthetic_unit(first)
+        inp = torch.cat([inp, _cases.synthetic_unit(first + 1)]).to(dev)
+        z = torch.randn(128, 31, 16, generator=g).to(dev)
+        a = engine.greedy_units(net, inp, 2, n_std, noise=z, decoder=eager).clone()
+        b = engine.greedy_units(net, inp, 2, n_std, noise=z, decoder=graphed).clone()
+        assert torch.equal(a, b)
+    assert graphed.launches > 100
