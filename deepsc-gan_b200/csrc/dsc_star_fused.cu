@@ -18,10 +18,15 @@
 // are don't-care.  Accumulators alternate between two 128-column TMEM buffers (J7 -> buffer 0, J8 -> buffer 1), so the UMMA of job j+1 overlaps the
 // epilogue of job j wherever the data dependence allows (all of J0..J3, J5/J6, and J0 of the next cycle under J8).
 //
-// Tried and dropped (round 1): keeping TWO tiles per CTA on the same 8 compute warps (ATT held in registers, relay GEMV
-// operands patched into the X operand, accumulators ping-ponged between the tiles).  Correct, but 1.9x slower: the
-// kernel is bound by the latency of the register-side work (tcgen05.ld -> shuffles -> tcgen05.st chains at 2 warps per
-// scheduler), not by UMMA latency, and the extra live state spilled.  The next step is more compute warps per tile.
+// Where the time goes (ncu, 2,368 sentences, 8 cycles, 545 us): a cycle is a serial chain of 9 hand-offs
+// UMMA (6.3 us of tensor time per tile and cycle) -> tcgen05.ld of the accumulators (TMEM reads run at 64 B/clk:
+// 580 KB = 4.6 us per tile and cycle) -> register work -> operand re-stage -> next UMMA, ~17 us per tile and cycle, so
+// the tensor pipe is busy ~37 % of the time.  Tried in round 1 and dropped, all parity-correct: (a) 8 instead of 16
+// compute warps: same time (the chain is latency-, not issue-bound); (b) two tiles per CTA on the same warps with ATT
+// held in registers: 1.9x slower (spills); (c) two tile pipelines per CTA (8 warps each, ATT in shared memory as an
+// SS-mode operand, single accumulator per tile, shared weight ring, in-order UMMA issue): 1.3x slower - with a shared
+// weight chunk the two tiles fall into lock-step (both UMMAs, then both epilogues) instead of alternating.  What is left
+// for round 2: out-of-order issue over a deeper ring, or cta_group::2 pairs sharing the streamed weights.
 //
 // Warps: 0-15 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, sub = warp >> 2 the column quarter),
 // 16 = UMMA issuer, 17 = weight producer.  The register-side work is latency-bound (tcgen05.ld -> shuffles ->
@@ -526,6 +531,7 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
               aligned16(bias_o) && aligned16(bias_o_relay) && aligned16(x_rowmajor), "dsc_star_cycles_tc: misaligned pointer");
   DSC_REQUIRE((((uintptr_t)packed_wqkv_grouped | (uintptr_t)packed_wo | (uintptr_t)packed_wkv_relay | (uintptr_t)packed_wo_relay |
                 (uintptr_t)packed_wq_relay) & 127u) == 0, "dsc_star_cycles_tc: packed weights must be 128-byte aligned");
+  prec &= 255;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_cycles_tc: prec must be 1 (bf16x3) or 2 (bf16)");
   if (n_sent == 0) return DSC_OK;
   if (n2 == 0) kv2 = kv_e;        // rows are read but masked (lane < n2 is false): any readable [n_sent][64][32][4] floats do

@@ -38,9 +38,8 @@ def timeit(name, fn, reps=10, cold=False):
 
 xrow = torch.empty(S * 4096, device=dev)
 for cyc in (1, 8):
-    for cold in (False, True):
-        timeit(f"star_cycles_tc x{cyc} n2={n2}", lambda: L.star_cycles_tc(xi, s_buf, q_r, kvei, kv2i, n2, w_g, wo, wkv_r, wo_r, wq_r,
-                                                                          bo, bo_r, xrow, S, cyc, prec), cold=cold)
+    timeit(f"star_cycles_tc x{cyc} n2={n2}", lambda: L.star_cycles_tc(xi, s_buf, q_r, kvei, kv2i, n2, w_g, wo, wkv_r, wo_r, wq_r,
+                                                                      bo, bo_r, xrow, S, cyc, prec), cold=True)
 if "--dbg" in sys.argv:
     for dbg in (0, 1, 2, 4, 1 | 2, 1 | 4, 2 | 4, 7):
         timeit(f"star_sat_tc dbg={dbg}", lambda: L.star_sat_tc(xi, s_buf, kvei, w_g, atti, S, prec | (dbg << 8)))
