@@ -25,7 +25,9 @@
 // compute warps: same time (the chain is latency-, not issue-bound); (b) two tiles per CTA on the same warps with ATT
 // held in registers: 1.9x slower (spills); (c) two tile pipelines per CTA (8 warps each, ATT in shared memory as an
 // SS-mode operand, single accumulator per tile, shared weight ring, in-order UMMA issue): 1.3x slower - with a shared
-// weight chunk the two tiles fall into lock-step (both UMMAs, then both epilogues) instead of alternating.  What is left
+// weight chunk the two tiles fall into lock-step (both UMMAs, then both epilogues) instead of alternating; (d) folding the
+// relay-query GEMV into the K|V phase (accumulated in the idle ATT columns): 6 % slower, the separate J8 already hides
+// under the next cycle's first QKV job.  What is left
 // for round 2: out-of-order issue over a deeper ring, or cta_group::2 pairs sharing the streamed weights.
 //
 // Warps: 0-15 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, sub = warp >> 2 the column quarter),
