@@ -65,8 +65,8 @@ _SIGNATURES = {
     "dsc_unit_dot": (C.c_int, [vp, vp, vp, i32, i64, vp]),
     "dsc_power_normalize_backward": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, i64, vp]),
     "dsc_channel_backward": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, i32, i64, vp]),
-    "dsc_dropout": (C.c_int, [vp, vp, f32, u64, u64, i64, vp]),
-    "dsc_adam_step": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, f32, f32, i32, f32, f32, i64, vp]),
+    "dsc_dropout": (C.c_int, [vp, vp, f32, u64, u64, vp, i64, vp]),
+    "dsc_adam_step": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, f32, f32, i32, vp, i32, f32, f32, i64, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -173,6 +173,12 @@ _PACK_CACHE = {}
 WEIGHT_EPOCH = 0
 
 
+# device-side count of completed training steps (int64 scalar tensor) while a graph-replayed training step is being
+# captured / replayed; None otherwise.  The dropout and Adam kernels read it (see include/deepsc_b200.h).
+STEP_DEV = None
+ADAM_APPLIES_PER_STEP = 1
+
+
 def weights_changed() -> None:
     global WEIGHT_EPOCH
     WEIGHT_EPOCH += 1
@@ -210,6 +216,8 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: 
     if out is None:
         out = torch.empty((M, N), device=x.device, dtype=torch.float32)
     assert out.dim() == 2 and out.shape[0] == M and out.shape[1] == N and out.stride(1) == 1
+    if M == 0:                       # empty batch: torch hands out a null data_ptr, nothing to launch
+        return out
     if prec != 0 and K % 128 == 0:
         blob = packed_weight(w, N)
         with _timed("dsc_linear_tc", (M, K, N)):
@@ -496,6 +504,8 @@ def bleu_counts(ref: torch.Tensor, hyp: torch.Tensor) -> torch.Tensor:
     assert ref.dtype == torch.int32 and hyp.dtype == torch.int32 and ref.is_contiguous() and hyp.is_contiguous()
     n = ref.shape[0]
     out = torch.empty((n, 10), device=ref.device, dtype=torch.int32)
+    if n == 0:
+        return out
     _check(load().dsc_bleu_counts(ref.data_ptr(), ref.shape[1], hyp.data_ptr(), hyp.shape[1], out.data_ptr(), n,
                                   _stream()), "dsc_bleu_counts")
     return out

@@ -305,16 +305,19 @@ class Dropout(torch.autograd.Function):
     def forward(ctx, x, rate: float, seed: int, offset: int):
         x = _c(x)
         out = torch.empty_like(x)
-        _check(load().dsc_dropout(x.data_ptr(), out.data_ptr(), rate, seed, offset, x.numel(), _stream()), "dsc_dropout")
-        ctx.args = (rate, seed, offset)
+        step_dev = _lib.STEP_DEV
+        _check(load().dsc_dropout(x.data_ptr(), out.data_ptr(), rate, seed, offset, _ptr(step_dev), x.numel(), _stream()),
+               "dsc_dropout")
+        ctx.args = (rate, seed, offset, step_dev)
         return out
 
     @staticmethod
     def backward(ctx, dy):
         dy = _c(dy)
         dx = torch.empty_like(dy)
-        rate, seed, offset = ctx.args
-        _check(load().dsc_dropout(dy.data_ptr(), dx.data_ptr(), rate, seed, offset, dy.numel(), _stream()), "dsc_dropout")
+        rate, seed, offset, step_dev = ctx.args
+        _check(load().dsc_dropout(dy.data_ptr(), dx.data_ptr(), rate, seed, offset, _ptr(step_dev), dy.numel(), _stream()),
+               "dsc_dropout")
         return dx, None, None, None
 
 
@@ -327,5 +330,6 @@ def adam_step(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch
         assert t.is_contiguous() and t.numel() == param.numel()
     assert grad2 is None or (grad2.is_contiguous() and grad2.numel() == param.numel())
     _check(load().dsc_adam_step(param.data_ptr(), grad.data_ptr(), _ptr(grad2), m.data_ptr(), v.data_ptr(), lr, beta1, beta2,
-                                eps, step, grad_scale, grad2_scale, param.numel(), _stream()), "dsc_adam_step")
+                                eps, step, _ptr(_lib.STEP_DEV), _lib.ADAM_APPLIES_PER_STEP, grad_scale, grad2_scale,
+                                param.numel(), _stream()), "dsc_adam_step")
     _lib.weights_changed()

@@ -575,7 +575,9 @@ __device__ __forceinline__ uint4 philox4(uint64_t ctr_lo, uint64_t ctr_hi, uint6
   return make_uint4(c0, c1, c2, c3);
 }
 __global__ void __launch_bounds__(256)
-dropout_kernel(const float4* __restrict__ x, float4* __restrict__ out, float rate, uint64_t seed, uint64_t offset, int64_t n4) {
+dropout_kernel(const float4* __restrict__ x, float4* __restrict__ out, float rate, uint64_t seed, uint64_t offset,
+               const int64_t* __restrict__ step_dev, int64_t n4) {
+  if (step_dev != nullptr) offset += (uint64_t)(*step_dev) << 20;          // a fresh mask per (graph-replayed) step
   const float keep_scale = 1.0f / (1.0f - rate);
   const uint32_t thresh = (uint32_t)(rate * 4294967296.0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -591,7 +593,12 @@ dropout_kernel(const float4* __restrict__ x, float4* __restrict__ out, float rat
 // p -= lr * sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, const float* __restrict__ g2, float* __restrict__ m,
-            float* __restrict__ v, float lr_t, float b1, float b2, float eps, float grad_scale, float grad2_scale, int64_t n) {
+            float* __restrict__ v, float lr_t, float lr, int step, const int64_t* __restrict__ step_dev, int steps_per_iter,
+            float b1, float b2, float eps, float grad_scale, float grad2_scale, int64_t n) {
+  if (step_dev != nullptr) {             // graph replay: the iteration count lives on the device
+    const double t = (double)step + (double)(*step_dev) * (double)steps_per_iter;
+    lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale;
     if (g2 != nullptr) gi = fmaf(g2[i], grad2_scale, gi);
@@ -793,20 +800,23 @@ extern "C" int dsc_channel_backward(const float* dy, const float* h, const float
   return check_launch("dsc_channel_backward");
 }
 
-extern "C" int dsc_dropout(const float* x, float* out, float rate, uint64_t seed, uint64_t offset, int64_t n, void* stream) {
+extern "C" int dsc_dropout(const float* x, float* out, float rate, uint64_t seed, uint64_t offset, const int64_t* step_dev,
+                           int64_t n, void* stream) {
   DSC_REQUIRE(x && out && n >= 0 && (n & 3) == 0 && aligned16(x) && aligned16(out), "dsc_dropout: n must be a multiple of 4, 16-byte aligned tensors");
   DSC_REQUIRE(rate >= 0.f && rate < 1.f, "dsc_dropout: rate must be in [0, 1)");
   if (n == 0) return DSC_OK;
   dropout_kernel<<<stream_blocks(n / 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out),
-                                                                    rate, seed, offset, n / 4);
+                                                                    rate, seed, offset, step_dev, n / 4);
   return check_launch("dsc_dropout");
 }
 
 extern "C" int dsc_adam_step(float* param, const float* grad, const float* grad2, float* m, float* v, float lr, float beta1,
-                             float beta2, float eps, int step, float grad_scale, float grad2_scale, int64_t n, void* stream) {
+                             float beta2, float eps, int step, const int64_t* step_dev, int steps_per_iter,
+                             float grad_scale, float grad2_scale, int64_t n, void* stream) {
   DSC_REQUIRE(param && grad && m && v && n >= 0 && step >= 1, "dsc_adam_step: bad argument");
   if (n == 0) return DSC_OK;
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, step)) / (1.0 - pow((double)beta1, step));
-  adam_kernel<<<stream_blocks(n), 256, 0, as_stream(stream)>>>(param, grad, grad2, m, v, (float)lr_t, beta1, beta2, eps, grad_scale, grad2_scale, n);
+  adam_kernel<<<stream_blocks(n), 256, 0, as_stream(stream)>>>(param, grad, grad2, m, v, (float)lr_t, lr, step, step_dev, steps_per_iter,
+                                                                beta1, beta2, eps, grad_scale, grad2_scale, n);
   return check_launch("dsc_adam_step");
 }

@@ -291,13 +291,18 @@ int dsc_channel_backward(const float* dy, const float* h, const float* n_std, in
 
 /* tf.keras.layers.Dropout in training mode (models/modules.py:179-183, 220, 246-250, 424-428, 458-466, 505, 546):
  * out = keep ? x / (1 - rate) : 0 with a Philox4x32-10 keep mask keyed by (seed, offset, element); calling it on dy
- * with the same (seed, offset) is the backward pass.  n % 4 == 0. */
-int dsc_dropout(const float* x, float* out, float rate, uint64_t seed, uint64_t offset, int64_t n, void* stream);
+ * with the same (seed, offset) is the backward pass.  n % 4 == 0.  step_dev (NULL = none): a device-side step counter
+ * mixed into the offset, so that a CUDA-graph replay of a training step draws fresh masks. */
+int dsc_dropout(const float* x, float* out, float rate, uint64_t seed, uint64_t offset, const int64_t* step_dev,
+                int64_t n, void* stream);
 
 /* One tf.keras.optimizers.Adam update on a flat fp32 buffer: g = grad * grad_scale (+ grad2 * grad2_scale when
- * grad2 != NULL, the lambda-mix of utlis/gan_train.py:22); m, v moments; step >= 1 is the optimizer's iteration count. */
+ * grad2 != NULL, the lambda-mix of utlis/gan_train.py:22); m, v moments; step >= 1 is the optimizer's iteration count.
+ * step_dev (NULL = none): device-side count of completed training steps; the iteration count used for the bias
+ * correction is then step + *step_dev * steps_per_iter (CUDA-graph replay of a step with steps_per_iter applies). */
 int dsc_adam_step(float* param, const float* grad, const float* grad2, float* m, float* v, float lr, float beta1,
-                  float beta2, float eps, int step, float grad_scale, float grad2_scale, int64_t n, void* stream);
+                  float beta2, float eps, int step, const int64_t* step_dev, int steps_per_iter,
+                  float grad_scale, float grad2_scale, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -515,3 +515,30 @@ def test_training_with_dropout_and_attack_step_run(dev):
     assert math.isfinite(float(loss)) and math.isfinite(float(loss_m)) and opt.iterations == 1
     moved = (opt.fp.flat - before).abs()
     assert float(moved.max()) > 1e-5 and float(moved.max()) < 1e-3            # one Adam step of lr 5e-4
+
+
+def test_graph_replayed_gan_train_step(dev):
+    """GraphedGanTrainStep: one CUDA-graph launch per step; Adam's bias correction and the dropout masks follow the
+    device-side step counter; training on a repeated batch lowers the clean-branch loss; optimizer iterations advance by
+    three per step as in the reference (three apply_gradients calls)."""
+    import deepsc_gan_b200.models.modules as Mod
+    from deepsc_gan_b200.utlis import gan_train as GT
+    args, gan = build("Transeiver_GAN", dev)
+    gan.train()
+    opt = GT.make_optimizer(gan)
+    inp = _cases.synthetic_unit(8).to(dev)
+    step = GT.GraphedGanTrainStep(gan, opt, 0.5, n_std=O.snr_to_noise(3.0), traingan=True, warmup=2)
+    losses = []
+    for i in range(8):
+        before = opt.fp.flat.clone()
+        loss, g_loss, d_loss = step(inp, inp)
+        losses.append(float(loss))
+        assert math.isfinite(losses[-1]) and math.isfinite(float(g_loss)) and math.isfinite(float(d_loss))
+        moved = (opt.fp.flat - before).abs().max()
+        assert 1e-6 < float(moved) < 5e-3, (i, float(moved))
+    assert opt.iterations == 3 * step.steps and step.steps == 10 and int(step.step_dev) == 8
+    assert losses[-1] < losses[0]
+    # the eager path still works afterwards and sees the updated weights (cache epoch bumped after every replay)
+    Mod.set_dropout_seed(1)
+    out = GT.gan_train_step(inp, inp, None, gan, opt, 0.5, channel="AWGN", n_std=O.snr_to_noise(3.0), training=True, traingan=True)
+    assert math.isfinite(float(out[0])) and float(out[0]) < losses[0] + 0.5
