@@ -88,9 +88,12 @@ def main():
         opt = GT.make_optimizer(net, learning_rate=cfg.lr)
         one = inp[:64]
         ns3 = float(sweep.snr_to_noise(3.0))
-        emit(5, "gan_train_step (Transeiver_GAN, traingan=True, lambda 0.5, dropout 0.1, Adam), one 64-unit per step",
+        emit(5, "gan_train_step eager (Transeiver_GAN, traingan=True, lambda 0.5, dropout 0.1, Adam), one 64-unit per step",
              timed(lambda: GT.gan_train_step(one, one, None, net, opt, 0.5, channel="AWGN", n_std=ns3, training=True,
-                                             traingan=True), max(args.steps, 5)), 64)
+                                             traingan=True), max(args.steps, 10), warmup=5), 64)
+        step = GT.GraphedGanTrainStep(net, opt, 0.5, n_std=ns3, traingan=True)
+        emit(5, "gan_train_step as one CUDA-graph launch per step (GraphedGanTrainStep), one 64-unit per step",
+             timed(lambda: step(one, one), max(args.steps, 20), warmup=3), 64)
 
 
 if __name__ == "__main__":
