@@ -35,6 +35,7 @@ _SIGNATURES = {
     "dsc_star_interleave": (C.c_int, [vp, i64, vp, i32, i32, i32, vp]),
     "dsc_star_kv2_put": (C.c_int, [vp, vp, i32, i32, vp]),
     "dsc_star_mix_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
+    "dsc_target_tail_tc": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, i64, i32, i32, vp]),
     "dsc_star_relay_update": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp]),
     "dsc_star_cycles_tc": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "dsc_star_relay_attn": (C.c_int, [vp, vp, i32, i32, vp, i32, vp]),
@@ -332,6 +333,24 @@ def star_cycles_tc(xi0: torch.Tensor, s0: torch.Tensor, q0: torch.Tensor, kvei: 
                                          bias_o_relay.data_ptr(), x_rowmajor.data_ptr(), n_sent, n_cycles, prec, _stream()),
                "dsc_star_cycles_tc")
     return x_rowmajor
+
+
+def target_tail_tc(attn: torch.Tensor, resid: torch.Tensor, wo: torch.Tensor, bias_o: torch.Tensor, gamma: torch.Tensor,
+                   beta: torch.Tensor, wkv_relay: torch.Tensor, kv2i: Optional[torch.Tensor], row_index: int, prec: int,
+                   kv_rows: Optional[torch.Tensor] = None, h2_out: Optional[torch.Tensor] = None) -> None:
+    """Fused Dense + residual + LayerNorm + relay k|v projection + key-cache write (include/deepsc_b200.h)."""
+    _need_cuda(attn, resid, wo, bias_o, gamma, beta, wkv_relay, kv2i, kv_rows, h2_out)
+    M = attn.shape[0]
+    assert attn.dim() == 2 and attn.shape[1] == 128 and attn.stride(1) == 1 and resid.shape == attn.shape and resid.stride(1) == 1
+    assert kv2i is None or (kv2i.is_contiguous() and kv2i.numel() == M * 8192)
+    assert kv_rows is None or (kv_rows.shape == (M, 256) and kv_rows.stride(1) == 1)
+    assert h2_out is None or (h2_out.shape == (M, 128) and h2_out.stride(1) == 1)
+    _check(load().dsc_target_tail_tc(attn.data_ptr(), attn.stride(0), resid.data_ptr(), resid.stride(0),
+                                     packed_weight(wo, 128).data_ptr(), bias_o.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                     packed_weight(wkv_relay, 256).data_ptr(), _ptr(kv2i), row_index,
+                                     _ptr(kv_rows), 0 if kv_rows is None else kv_rows.stride(0),
+                                     _ptr(h2_out), 0 if h2_out is None else h2_out.stride(0), M, prec, _stream()),
+           "dsc_target_tail_tc")
 
 
 def star_relay_update(att_r: torch.Tensor, wo: torch.Tensor, bo: torch.Tensor, wq: torch.Tensor, s_out: torch.Tensor,

@@ -40,6 +40,9 @@ vocab_argmax_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* 
   __shared__ __align__(8) Bars bars;
   __shared__ uint32_t tmem_base_s;
   __shared__ int last_flag;
+  // per epilogue warp, double-buffered: the 64 bias values of a vocabulary tile (16 lanes fetch one float4 each a tile
+  // ahead; every lane then reads them as shared-memory broadcasts instead of issuing 16 global loads per tile)
+  __shared__ __align__(16) float bias_s[kEpiWarps][2][BN];
   constexpr int parts = (NPASS == 3) ? 2 : 1;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -86,8 +89,25 @@ vocab_argmax_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* 
     // ---- running argmax over this CTA's vocabulary tiles
     float best = -INFINITY;
     int best_idx = 0x7fffffff;
+    auto fetch_bias = [&](int i) {                 // tile i of this CTA -> bias_s[warp][i & 1]; columns >= N read as 0
+      if (lane < 16) {
+        const int c0 = (j0 + i) * BN + 4 * lane;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + 3 < N) b4 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+        else {
+          if (c0 < N) b4.x = __ldg(bias + c0);
+          if (c0 + 1 < N) b4.y = __ldg(bias + c0 + 1);
+          if (c0 + 2 < N) b4.z = __ldg(bias + c0 + 2);
+        }
+        reinterpret_cast<float4*>(&bias_s[warp][i & 1][0])[lane] = b4;
+      }
+    };
+    if (my_tiles > 0) fetch_bias(0);
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
+      __syncwarp();                                // bias of tile i is in place; the buffer of tile i + 1 is free
+      if (i + 1 < my_tiles) fetch_bias(i + 1);
+      const float4* bs = reinterpret_cast<const float4*>(&bias_s[warp][b][0]);
       mbar_wait(&bars.acc_full[b], (i >> 1) & 1);
       tc_fence_after();
       float v[64];
@@ -100,7 +120,7 @@ vocab_argmax_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* 
       if (n0 + BN <= N) {
 #pragma unroll
         for (int c4 = 0; c4 < 16; ++c4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0) + c4);
+          const float4 b4 = bs[c4];
           const float t0 = v[4 * c4] + b4.x, t1 = v[4 * c4 + 1] + b4.y, t2 = v[4 * c4 + 2] + b4.z, t3 = v[4 * c4 + 3] + b4.w;
           if (t0 > best) { best = t0; best_idx = n0 + 4 * c4; }
           if (t1 > best) { best = t1; best_idx = n0 + 4 * c4 + 1; }
@@ -109,7 +129,7 @@ vocab_argmax_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* 
         }
       } else {
         for (int c = 0; c < BN && n0 + c < N; ++c) {
-          const float t = v[c] + __ldg(bias + n0 + c);
+          const float t = v[c] + bias_s[warp][b][c];
           if (t > best) { best = t; best_idx = n0 + c; }
         }
       }

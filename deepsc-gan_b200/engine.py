@@ -69,6 +69,7 @@ class _StarLayerState:
         self.kv2 = torch.empty((n_sent, max_len, 256), **f)      # k|v of h2 rows under the relay weights
         self.kv2i = torch.zeros((n_sent * 8192,), **f)           # same cache, interleaved (tcgen05 path)
         self.kv2_row = torch.empty((n_sent, 256), **f)
+        self.att_o = torch.empty((n_sent, 1, 128), **f)          # multi_tar attention output of the newest row
         self.ws = StarWorkspace(n_sent, device)
         self.tile = torch.empty((n_sent, 32, 128), **f)
 
@@ -109,14 +110,18 @@ class StarGreedyDecoder:
             for li, st in enumerate(self.layers):
                 L = st.layer
                 _lib.linear(x2, L.multi_tar._packed("qkv"), None, out=st.qkv_tar[:, t, :], prec=M.PREC)
-                a = L.multi_tar.attend(st.qkv_tar[:, t:t + 1, 0:128], st.qkv_tar[:, :t + 1, 128:256],
-                                       st.qkv_tar[:, :t + 1, 256:384],
-                                       key_ids=self.outputs)           # causal: the newest row sees the whole prefix
-                h2_t = _add_ln(a, x_t, L.layernorm1)
                 if tc:
-                    _lib.linear(h2_t.view(S, 128), st.relay._packed("kv"), None, out=st.kv2_row, prec=M.PREC)
-                    _lib.star_kv2_put(st.kv2_row, st.kv2i, t)
+                    # causal: the newest row sees the whole prefix.  Attention, then ONE kernel for dense + residual +
+                    # LayerNorm1 + relay k|v projection + key-cache write
+                    _lib.mha_attention(st.qkv_tar[:, t:t + 1, 0:128], st.qkv_tar[:, :t + 1, 128:256],
+                                       st.qkv_tar[:, :t + 1, 256:384], st.att_o, key_ids=self.outputs)
+                    _lib.target_tail_tc(st.att_o.view(S, 128), x2, L.multi_tar.dense.kernel.detach(),
+                                        L.multi_tar.dense.bias.detach(), L.layernorm1.gamma.detach(),
+                                        L.layernorm1.beta.detach(), st.relay._packed("kv"), st.kv2i, t, M.PREC)
                 else:
+                    a = L.multi_tar.attend(st.qkv_tar[:, t:t + 1, 0:128], st.qkv_tar[:, :t + 1, 128:256],
+                                           st.qkv_tar[:, :t + 1, 256:384], key_ids=self.outputs)
+                    h2_t = _add_ln(a, x_t, L.layernorm1)
                     _lib.linear(h2_t.view(S, 128), st.relay._packed("kv"), None, out=st.kv2[:, t, :], prec=M.PREC)
                 if li > 0:                                             # memory of layer li = output of layer li-1
                     _lib.star_pack(self.mid, st.tile)

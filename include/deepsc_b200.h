@@ -134,6 +134,17 @@ int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, c
                        const float* bias_o, const float* bias_o_relay,
                        float* x_rowmajor, int n_sent, int n_cycles, int prec, void* stream);
 
+/* Tail of the causal target branch of a star decoder step (models/modules.py:352-354 and the relay k|v projection of
+ * :375-377), fused: h2 = LayerNorm(resid + attn @ wo + bias_o; gamma, beta), k|v = h2 @ [wk|wv]_relay, written to row
+ * `row_index` of the interleaved key cache kv2 [M][64][32][4] (NULL: skipped) and/or row-major to kv_rows [M,256]
+ * (NULL: skipped); h2_out [M,128] optional.  attn = attention output before the dense layer.  packed_* =
+ * dsc_pack_weight images of the [128,128] / [128,256] kernels. */
+int dsc_target_tail_tc(const float* attn, int64_t ld_attn, const float* resid, int64_t ld_resid,
+                       const void* packed_wo, const float* bias_o, const float* gamma, const float* beta,
+                       const void* packed_wkv_relay, float* kv2, int row_index,
+                       float* kv_rows, int64_t ld_kv, float* h2_out, int64_t ld_h2,
+                       int M, int prec, void* stream);
+
 /* relay node update: s_out = relu(att_relay @ wo + bo) (models/modules.py:305-306), q_out = s_out @ wq (the next
  * cycle's relay query).  fp32 FFMA, weights Keras layout [128,128] contiguous, all tensors [n_sent,128]. */
 int dsc_star_relay_update(const float* att_relay, const float* wo, const float* bo, const float* wq,

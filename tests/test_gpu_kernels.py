@@ -415,3 +415,28 @@ def test_star_interleave_layout(L, dev):
     L.star_kv2_put(vals, kv2i, 7)
     assert torch.equal(kv2i.view(5, 64, 32, 4)[:, :, 7, :].reshape(5, 256), vals)
     assert float(kv2i.view(5, 64, 32, 4)[:, :, 8, :].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("prec,tol", [(1, 1e-4), (2, 3e-2)])
+def test_target_tail_fused(L, dev, prec, tol):
+    """dsc_target_tail_tc = Dense + residual + LayerNorm + relay k|v projection + key-cache row write, against the
+    same chain in fp64; ragged M (not a multiple of the 128-row tile)."""
+    g = torch.Generator().manual_seed(77)
+    Mrows = 200
+    attn, resid = torch.randn(Mrows, 128, generator=g), torch.randn(Mrows, 128, generator=g)
+    wo, bo = torch.randn(128, 128, generator=g) * 0.1, torch.randn(128, generator=g) * 0.1
+    gamma, beta = torch.rand(128, generator=g) + 0.5, torch.randn(128, generator=g) * 0.1
+    wkv = torch.randn(128, 256, generator=g) * 0.1
+    h = resid.double() + attn.double() @ wo.double() + bo.double()
+    h2 = (h - h.mean(-1, keepdim=True)) / torch.sqrt(h.var(-1, unbiased=False, keepdim=True) + 1e-6) * gamma.double() + beta.double()
+    kv = h2 @ wkv.double()
+    kv2i = torch.zeros(Mrows * 8192, device=dev)
+    rows = torch.empty(Mrows, 256, device=dev)
+    h2_out = torch.empty(Mrows, 128, device=dev)
+    L.target_tail_tc(attn.to(dev), resid.to(dev), wo.to(dev), bo.to(dev), gamma.to(dev), beta.to(dev), wkv.to(dev), kv2i, 9,
+                     prec, kv_rows=rows, h2_out=h2_out)
+    torch.cuda.synchronize()
+    assert rel_err(h2_out, h2) < tol and rel_err(rows, kv) < tol
+    cache = kv2i.view(Mrows, 64, 32, 4)
+    assert torch.equal(cache[:, :, 9, :].reshape(Mrows, 256), rows)
+    assert float(cache[:, :, 8, :].abs().max()) == 0.0 and float(cache[:, :, 10, :].abs().max()) == 0.0
