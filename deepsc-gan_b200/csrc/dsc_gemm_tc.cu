@@ -102,11 +102,13 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
     }
     fence_async_smem();
     __syncthreads();
-    // ---- MMA issue (one thread)
-    if (tid == 0) {
+    // ---- MMA issue: warp 0 converged, one elected lane issues (dsc_tc.cuh elect_one)
+    if (warp == 0) {
+      const bool leader = elect_one();
       mbar_wait(&bar_b, c & 1);
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      if (leader) {
 #pragma unroll
       for (int pass = 0; pass < NPASS; ++pass) {
         const int pa = (pass == 1) ? 1 : 0;                   // pass 0: hi*hi, pass 1: lo*hi, pass 2: hi*lo
@@ -121,6 +123,8 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
           }
       }
       umma_commit(&bar_mma);
+      }
+      __syncwarp();
     }
   }
   // ---- epilogue: TMEM -> registers -> bias/act -> global

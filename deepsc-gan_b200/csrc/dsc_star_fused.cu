@@ -157,7 +157,11 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     __syncwarp();
   } else if (warp == sf::kMmaWarp) {
     // ------------------------------------------------------------------ UMMA issuer
-    if (lane == 0) {
+    // The whole warp runs the job loop in lock-step and ONE elected lane issues: tcgen05.mma / commit issued from a
+    // divergent `if (lane == 0)` region cost ~94 cycles each (compiler-generated elect loop), from here 58 (N = 96) and
+    // 74 (N = 128) cycles (tools/umma_probe.py).
+    {
+      const bool leader = elect_one();
       const uint32_t ring_base = smem_u32(ring);
       uint32_t n = 0, use0 = 0, use1 = 0, xr = 0, tr = 0;  // chunks consumed, accumulator uses, operand phases consumed
       for (int t = 0; t < my_tiles; ++t)
@@ -174,15 +178,17 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             const uint32_t bb = ring_base + st * STAGE_BYTES;
             const uint32_t acc = b ? ACC1 : ACC0;
             const bool from_t = (j == 4 || j >= 7);
-            if (j < 4) issue_group<NPASS, 96>(tmem_base, acc, AX_HI, AX_LO, bb, 96u * 128u, 0u);
-            else if (from_t) issue_group<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0u);
-            else issue_group<NPASS, 128>(tmem_base, acc, AX_HI, AX_LO, bb, 128u * 128u, 0u);
-            umma_commit(&bars.w_free[st]);
-            umma_commit(&bars.acc_full[b]);
+            if (leader) {
+              if (j < 4) issue_group<NPASS, 96>(tmem_base, acc, AX_HI, AX_LO, bb, 96u * 128u, 0u);
+              else if (from_t) issue_group<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0u);
+              else issue_group<NPASS, 128>(tmem_base, acc, AX_HI, AX_LO, bb, 128u * 128u, 0u);
+              umma_commit(&bars.w_free[st]);
+              umma_commit(&bars.acc_full[b]);
+            }
+            __syncwarp();
           }
         }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ compute warps (16)
     // quarter = TMEM lane quarter = sentence of the tile; sub = column quarter (32 of the 128 columns, = heads 2*sub,

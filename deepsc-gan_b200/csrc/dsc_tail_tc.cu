@@ -82,9 +82,11 @@ tar_tail_kernel(const float* __restrict__ attn, int64_t ld_attn, const float* __
     }
     umma_commit(&bar_mma);
   };
-  if (tid == 0) {
+  if (warp == 0) {                       // warp 0 converged, one elected lane issues (dsc_tc.cuh elect_one)
+    const bool leader = elect_one();
     mbar_wait(&bar_wo, 0);
-    issue(smem_u32(sWo), WO_PLANE, 128);
+    if (leader) issue(smem_u32(sWo), WO_PLANE, 128);
+    __syncwarp();
   }
   // ---- epilogue 1: + bias + residual, LayerNorm over the thread's own 128 values, re-staged as A operand 2
   mbar_wait(&bar_mma, 0);
@@ -144,9 +146,11 @@ tar_tail_kernel(const float* __restrict__ attn, int64_t ld_attn, const float* __
   }
   tc_fence_before();
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0) {
+    const bool leader = elect_one();
     mbar_wait(&bar_wkv, 0);
-    issue(smem_u32(sWkv), WKV_PLANE, 256);
+    if (leader) issue(smem_u32(sWkv), WKV_PLANE, 256);
+    __syncwarp();
   }
   // ---- epilogue 2: k|v of the new h2 row -> cache
   mbar_wait(&bar_mma, 1);

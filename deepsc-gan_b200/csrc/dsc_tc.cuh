@@ -129,6 +129,20 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / tcgen05.commit take uniform-datapath operands: issued from a
+// divergent `if (lane == 0)` region the compiler wraps every one of them in an elect-and-loop sequence (~94 cycles per
+// UMMA measured, whatever its width); issued under this predicate from warp-uniform control flow they go out back to
+// back (tools/umma_probe.py).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- bf16 hi/lo split ---------------------------------------------------------------------------------
 // x = hi + lo + O(2^-17 |x|): hi = rn_bf16(x), lo = rn_bf16(x - hi).  Packs two values per 32-bit word.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {

@@ -128,9 +128,10 @@ vocab_argmax_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* 
           if (t3 > best) { best = t3; best_idx = n0 + 4 * c4 + 3; }
         }
       } else {
-        for (int c = 0; c < BN && n0 + c < N; ++c) {
+#pragma unroll
+        for (int c = 0; c < BN; ++c) {                 // static indices: v[] must stay in registers
           const float t = v[c] + bias_s[warp][b][c];
-          if (t > best) { best = t; best_idx = n0 + c; }
+          if (n0 + c < N && t > best) { best = t; best_idx = n0 + c; }
         }
       }
     }
@@ -153,7 +154,9 @@ vocab_argmax_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* 
   } else {
     asm volatile("bar.sync 1, %0;" :: "n"((kEpiWarps + 1) * 32) : "memory");      // A operands are in TMEM
     tc_fence_after();
-    if (lane == 0) {
+    {
+      // whole warp in lock-step, one elected lane issues (see dsc_tc.cuh elect_one: 42 instead of 94 cycles per N = 64 UMMA)
+      const bool leader = elect_one();
       constexpr uint32_t IDESC = idesc_bf16_f32(128, BN);
       const uint32_t b_base = smem_u32(sB);
       for (int i = 0; i < my_tiles; ++i) {
@@ -161,27 +164,29 @@ vocab_argmax_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* 
         mbar_wait(&bars.b_full[s], (i / STAGES) & 1);
         mbar_wait(&bars.acc_empty[b], ((i >> 1) - 1) & 1);
         tc_fence_after();
+        if (leader) {
 #pragma unroll
-        for (int mh = 0; mh < 2; ++mh) {
-          const uint32_t d = tmem_base + COL_ACC + (b * 2 + mh) * 64;
+          for (int mh = 0; mh < 2; ++mh) {
+            const uint32_t d = tmem_base + COL_ACC + (b * 2 + mh) * 64;
 #pragma unroll
-          for (int pass = 0; pass < NPASS; ++pass) {
-            const uint32_t a_col = COL_A + mh * 128 + ((pass == 1) ? 64u : 0u);       // hi*hi, lo*hi, hi*lo
-            const uint32_t pb = (pass == 2) ? 1u : 0u;
+            for (int pass = 0; pass < NPASS; ++pass) {
+              const uint32_t a_col = COL_A + mh * 128 + ((pass == 1) ? 64u : 0u);       // hi*hi, lo*hi, hi*lo
+              const uint32_t pb = (pass == 2) ? 1u : 0u;
 #pragma unroll
-            for (int kb = 0; kb < 2; ++kb)
+              for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t db = smem_desc_sw128(b_base + s * STAGE_BYTES + (pb * 2 + kb) * PLANE + ks * 32u);
-                umma_ts(d, tmem_base + a_col + (uint32_t)(kb * 4 + ks) * 8u, db, IDESC, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
-              }
+                for (int ks = 0; ks < 4; ++ks) {
+                  const uint64_t db = smem_desc_sw128(b_base + s * STAGE_BYTES + (pb * 2 + kb) * PLANE + ks * 32u);
+                  umma_ts(d, tmem_base + a_col + (uint32_t)(kb * 4 + ks) * 8u, db, IDESC, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+                }
+            }
           }
+          umma_commit(&bars.b_empty[s]);
+          umma_commit(&bars.acc_full[b]);
         }
-        umma_commit(&bars.b_empty[s]);
-        umma_commit(&bars.acc_full[b]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   }
 
   // ---- cross-CTA fold: the last CTA of this m-tile to arrive writes the ids

@@ -315,6 +315,10 @@ int dsc_adam_step(float* param, const float* grad, const float* grad2, float* m,
                   float beta2, float eps, int step, const int64_t* step_dev, int steps_per_iter,
                   float grad_scale, float grad2_scale, int64_t n, void* stream);
 
+/* Micro-benchmark (not on the product path): cycles for iters x 8 back-to-back tcgen05.mma (M = 128, K = 16, width n) with
+ * the A operand in tensor memory (ts_mode != 0) or shared memory; result in cycles_dev[0]. */
+int dsc_umma_probe(int ts_mode, int n, int iters, long long* cycles_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
