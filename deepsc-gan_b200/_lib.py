@@ -68,6 +68,7 @@ _SIGNATURES = {
     "dsc_channel_backward": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, i32, i64, vp]),
     "dsc_dropout": (C.c_int, [vp, vp, f32, u64, u64, vp, i64, vp]),
     "dsc_umma_probe": (C.c_int, [i32, i32, i32, vp, vp]),
+    "dsc_debug_star_trace": (C.c_int, [vp]),
     "dsc_adam_step": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, f32, f32, i32, vp, i32, f32, f32, i64, vp]),
 }
 

@@ -7,32 +7,43 @@
 // tile's 256 KB of keys are touched every cycle.  The five weight matrices (512 KB as bf16 hi/lo planes) do not fit
 // in shared memory, so a producer thread streams them per job through a shared-memory ring with cp.async.bulk.
 //
-// Jobs of one cycle (one elected thread issues the UMMAs, M = 128, fp32 accumulators in TMEM):
-//   J0..J3  QKV of head pair g = X @ [Wq|Wk|Wv]_sat[g]          N = 96  -> satellite attention over the 5 keys
+// Jobs of one cycle (one elected thread issues the UMMAs, fp32 accumulators in TMEM):
+//   J0..J3  QKV of head pair g = X @ [Wq|Wk|Wv]_sat[g]          M = 128, N = 96  -> satellite attention over the 5 keys
 //                                                                          {h[i+1], h[i], h[i-1], e[i], s} -> ATT (TMEM)
 //   J4      O   = ATT @ Wo_sat                                   N = 128 -> X' = relu(O + b) (relay row keeps s) -> X (TMEM)
 //   J5, J6  K|V = X' @ [Wk|Wv]_relay                              N = 128 each -> relay attention over 32 (+n2) keys -> att_r
-//   J7      R1  = att_r @ Wo_relay                                N = 128 -> s' = relu(R1 + b) -> relay row of X patched
-//   J8      R2  = s' @ Wq_relay                                   N = 128 -> q' (the next cycle's relay query)
-// J7/J8 use only the relay lane of each sentence (lane 31 of a warp quarter); the other 124 rows of those two UMMAs
-// are don't-care.  Accumulators alternate between two 128-column TMEM buffers (J7 -> buffer 0, J8 -> buffer 1), so the UMMA of job j+1 overlaps the
-// epilogue of job j wherever the data dependence allows (all of J0..J3, J5/J6, and J0 of the next cycle under J8).
+//   J7      R1^T = Wo_relay^T @ att_r^T                           M = 128 features, N = 16 (4 sentences) -> s' = relu(R1 + b)
+//   J8      R2^T = Wq_relay^T @ s'^T                              same shape -> q' (the next cycle's relay query)
+// J7/J8 are GEMVs (one row per sentence).  As X @ W they would spend a full M = 128, N = 128 UMMA on 4 useful rows, so
+// they run transposed: the streamed weight chunk (K-major, the same image either way) is the A operand and the four
+// vectors, written as bf16 hi/lo into a 16-row K-major shared-memory operand, are B.  The result lands feature-major
+// (TMEM lane = feature, column = sentence): each compute thread reads ONE accumulator word, and s' / q' return to the
+// sentence-major consumers through shared memory and a named barrier of the compute warps.
+// Accumulators alternate between two 128-column TMEM buffers (J7 -> buffer 0, J8 -> buffer 1), so the UMMA of job j+1
+// overlaps the epilogue of job j wherever the data dependence allows (all of J0..J3, J5/J6, and J0 of the next cycle
+// under J8).
 //
-// Where the time goes (ncu, 2,368 sentences, 8 cycles, 545 us): a cycle is a serial chain of 9 hand-offs
-// UMMA (6.3 us of tensor time per tile and cycle) -> tcgen05.ld of the accumulators (TMEM reads run at 64 B/clk:
-// 580 KB = 4.6 us per tile and cycle) -> register work -> operand re-stage -> next UMMA, ~17 us per tile and cycle, so
-// the tensor pipe is busy ~37 % of the time.  Tried in round 1 and dropped, all parity-correct: (a) 8 instead of 16
-// compute warps: same time (the chain is latency-, not issue-bound); (b) two tiles per CTA on the same warps with ATT
-// held in registers: 1.9x slower (spills); (c) two tile pipelines per CTA (8 warps each, ATT in shared memory as an
-// SS-mode operand, single accumulator per tile, shared weight ring, in-order UMMA issue): 1.3x slower - with a shared
-// weight chunk the two tiles fall into lock-step (both UMMAs, then both epilogues) instead of alternating; (d) folding the
-// relay-query GEMV into the K|V phase (accumulated in the idle ATT columns): 6 % slower, the separate J8 already hides
-// under the next cycle's first QKV job.  What is left
-// for round 2: out-of-order issue over a deeper ring, or cta_group::2 pairs sharing the streamed weights.
+// Where the time goes (tools/star_trace.py: clock64 stamps of CTA 0 at every hand-off; 2,368 sentences, 8 cycles,
+// 494-508 us, 13.9 us per tile and cycle): J0..J3 until ATT is staged 5.4 us (2.5 us of tensor time; each QKV epilogue
+// holds its accumulator ~0.75 us, longer than its UMMA), J4 + its epilogue 2.3 us, J5/J6 + the relay attention 4.0 us,
+// J7/J8 + the relay-row patch 2.4 us.  Tensor time per tile and cycle is ~5.9 us at 1.965 GHz (24 UMMAs per job at
+// 58 / 74 cycles for N = 96 / 128, ~45 cycles for the N = 16 GEMVs), all of it on the critical path except J6 and J1..J3:
+// the pipe is busy ~36 % of the time (ncu sm__pipe_tensor_cycles_active), the compute warps are issue-bound inside each
+// epilogue burst (smsp__issue_active 33 % on average) and idle while the UMMAs run.
+// Tried in round 1 and dropped, all parity-correct: (a) 8 instead of 16 compute warps: same time in the spilling early
+// version, slower now; (b) two tiles per CTA on the same warps with ATT held in registers: 1.9x slower (spills);
+// (c) two tile pipelines per CTA (8 warps each, ATT in shared memory as an SS-mode operand, single accumulator per
+// tile, shared weight ring, in-order UMMA issue), re-measured after the elected-lane fix: 31 us per PAIR and cycle =
+// exactly two sequential tiles (562 vs 537 us): the tiles fall into lock-step, both epilogues contend for the same four
+// schedulers while the pipe idles, and the per-tile double buffering of J0..J3 is lost; (d) folding the relay-query GEMV
+// into the K|V phase: 6 % slower.  The transposed J7/J8 gave 537 -> ~500 us.
+// Next: a half-cycle phase offset between two resident tiles needs 640 TMEM columns (2 x (X 128 + ACC 128) + ATT 128),
+// so it has to come from splitting each N = 128 job into halves with their own commits (epilogue of half 0 under the
+// UMMA of half 1) and from caching cycle 1's J0..J4, which do not depend on the decoded prefix.
 //
 // Warps: 0-15 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, sub = warp >> 2 the column quarter),
-// 16 = UMMA issuer, 17 = weight producer.  The register-side work is latency-bound (tcgen05.ld -> shuffles ->
-// tcgen05.st chains), so it is spread over 4 warps per scheduler: every warp owns 32 of the 128 columns of a row.  Arithmetic as in dsc_star_tc.cu: prec 1 = bf16x3, 2 = bf16; fp32 softmax.
+// 16 = UMMA issuer, 17 = weight producer.  Every warp owns 32 of the 128 columns of a row.  Arithmetic as in
+// dsc_star_tc.cu: prec 1 = bf16x3, 2 = bf16; fp32 softmax.
 #include "dsc_star_common.cuh"
 
 namespace dsc {
@@ -45,6 +56,8 @@ constexpr int STAGES = 3;
 constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
 constexpr int JOBS = 9;
+constexpr uint32_t RB_PLANE = 16 * 128;                       // relay-vector operand: one (part, kb) plane = 16 rows x 128 B
+constexpr uint32_t RB_BYTES = 4 * RB_PLANE;                   // 8 KB behind the ring
 
 struct Bars {
   uint64_t w_full[STAGES], w_free[STAGES];
@@ -103,7 +116,40 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(n) : "memory");
 }
 
+// Debug timeline (tools/star_trace.py): when a buffer is registered with dsc_debug_star_trace, CTA 0 stamps clock64()
+// at the hand-offs of its first tile: issuer [0, 256) = (operands ready, UMMAs + commits issued) per job; compute warp 0
+// [256, 512) and warp 8 [512, 768) = their accumulator-seen / operand-staged events in program order.
+__device__ unsigned long long* g_star_trace = nullptr;
+#define DSC_TR(base) do { if (TRACE) { if (tr_buf && tr_n < 256) tr_buf[(base) + tr_n] = (unsigned long long)clock64(); ++tr_n; } } while (0)
+
+// relay GEMVs (J7, J8) in transposed form: D[feature][sentence] = W^T (A, the streamed chunk, M = 128) x vectors (B, N = 16
+// rows of which 4 are sentences).  passes: w_hi*v_hi, w_hi*v_lo, w_lo*v_hi - the same products in the same order as
+// issue_group's hi*hi, lo*hi, hi*lo with the activations as A.
 template <int NPASS>
+__device__ __forceinline__ void issue_relay_gemv(uint32_t d_tmem, uint32_t w_base, uint32_t v_base) {
+  constexpr uint32_t IDESC = idesc_bf16_f32(128, 16);
+#pragma unroll
+  for (int pass = 0; pass < NPASS; ++pass) {
+    const uint32_t pw = (pass == 2) ? 1u : 0u, pv = (pass == 1) ? 1u : 0u;
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        umma_ss(d_tmem, smem_desc_sw128(w_base + (pw * 2 + kb) * (128u * 128u) + ks * 32u),
+                smem_desc_sw128(v_base + (pv * 2 + kb) * sf::RB_PLANE + ks * 32u), IDESC, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+  }
+}
+__device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
+// one fp32 value -> bf16 hi / lo of element (row, k) of the relay-vector operand
+template <int NPASS>
+__device__ __forceinline__ void put_relay_operand(uint8_t* rb, int row, int k, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const uint32_t off = ((uint32_t)k >> 6) * sf::RB_PLANE + sw128_offset((uint32_t)row, (uint32_t)k & 63u);
+  *reinterpret_cast<__nv_bfloat16*>(rb + off) = h;
+  if (NPASS == 3) *reinterpret_cast<__nv_bfloat16*>(rb + 2 * sf::RB_PLANE + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+template <int NPASS, bool TRACE>
 __global__ void __launch_bounds__(sf::kThreads, 1)
 star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, const float* __restrict__ Q0,
                   const float* __restrict__ KVEI, const float* __restrict__ KV2I, int n2, sf::Weights W,
@@ -112,15 +158,20 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
   using namespace sf;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* rb = ring + STAGES * STAGE_BYTES;         // att_r, then s': B operand of the transposed relay GEMVs (rows 4..15 zero)
   __shared__ __align__(8) sf::Bars bars;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_cur[4][128];      // relay node of the 4 sentences of the tile
   __shared__ __align__(16) float q_cur[4][128];      // its query under the relay weights
-  __shared__ __align__(16) float attr[4][128];       // relay attention output
+  __shared__ __align__(16) uint32_t patch_w[2][4][4][16];   // [hi|lo][sentence][column quarter]: bf16 pairs of s' for the X patch
   constexpr int parts = (NPASS == 3) ? 2 : 1;
   constexpr uint32_t kArrivals = kCompute;            // one elected arrival per compute warp (after __syncwarp)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* tr_buf = (TRACE && blockIdx.x == 0 && (tid == sf::kMmaWarp * 32 || tid == 0 || tid == 256)) ? g_star_trace : nullptr;
+  int tr_n = 0;
+  for (uint32_t i = tid; i < RB_BYTES / 16; i += sf::kThreads) reinterpret_cast<uint4*>(rb)[i] = make_uint4(0, 0, 0, 0);
+  fence_async_smem();
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_free[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kArrivals); }
@@ -162,7 +213,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     // 74 (N = 128) cycles (tools/umma_probe.py).
     {
       const bool leader = elect_one();
-      const uint32_t ring_base = smem_u32(ring);
+      const uint32_t ring_base = smem_u32(ring), rb_base = smem_u32(rb);
       uint32_t n = 0, use0 = 0, use1 = 0, xr = 0, tr = 0;  // chunks consumed, accumulator uses, operand phases consumed
       for (int t = 0; t < my_tiles; ++t)
         for (int c = 0; c < n_cycles; ++c) {
@@ -175,16 +226,18 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             if (b) { mbar_wait(&bars.acc_free[1], (use1 - 1) & 1); ++use1; }
             else   { mbar_wait(&bars.acc_free[0], (use0 - 1) & 1); ++use0; }
             tc_fence_after();
+            if (t == 0) DSC_TR(0);
             const uint32_t bb = ring_base + st * STAGE_BYTES;
             const uint32_t acc = b ? ACC1 : ACC0;
-            const bool from_t = (j == 4 || j >= 7);
             if (leader) {
               if (j < 4) issue_group<NPASS, 96>(tmem_base, acc, AX_HI, AX_LO, bb, 96u * 128u, 0u);
-              else if (from_t) issue_group<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0u);
+              else if (j == 4) issue_group<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0u);
+              else if (j >= 7) issue_relay_gemv<NPASS>(tmem_base + acc, bb, rb_base);
               else issue_group<NPASS, 128>(tmem_base, acc, AX_HI, AX_LO, bb, 128u * 128u, 0u);
               umma_commit(&bars.w_free[st]);
               umma_commit(&bars.acc_full[b]);
             }
+            if (t == 0) DSC_TR(0);
             __syncwarp();
           }
         }
@@ -202,21 +255,23 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     const int dn = (lane == 0) ? 30 : lane - 1;                    // roll(h,+1)[i] = h[(i-1) mod 31]
     float* my_s = &s_cur[quarter][sub * 32];
     float* my_q = &q_cur[quarter][sub * 32];
-    float* my_attr = &attr[quarter][sub * 32];
     uint32_t use0 = 0, use1 = 0;                                   // accumulator phases seen (scalars: no local memory)
     auto wait_acc = [&](int b) {
       if (b) { mbar_wait(&bars.acc_full[1], use1 & 1); ++use1; } else { mbar_wait(&bars.acc_full[0], use0 & 1); ++use0; }
       tc_fence_after();
+      DSC_TR(warp ? 512 : 256);
     };
     // every lane fences its own TMEM accesses, the warp converges, one lane arrives for the warp
     auto warp_arrive = [&](uint64_t* bar, uint32_t n) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_n(bar, n);
+      DSC_TR(warp ? 512 : 256);
     };
     auto free_acc = [&](int b) { warp_arrive(&bars.acc_free[b], 1); };
 
     for (int ti = 0; ti < my_tiles; ++ti) {
+      if (ti) tr_buf = nullptr;
       const int t = blockIdx.x + ti * gridDim.x;
       const int64_t sent = (int64_t)t * 4 + quarter;
       const uint4* kve_base = reinterpret_cast<const uint4*>(KVEI + (int64_t)t * 32768) + row_in_tile;
@@ -356,6 +411,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
 #pragma unroll
           for (int i = 0; i < 8; ++i) k2[i] = __ldg(kv2 + i * 32);
           float w1[2], w2[2];
+          compute_warps_sync();                                      // q' (written feature-major by the J8 epilogue) is complete
           wait_acc(1);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -412,93 +468,79 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
                 p[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
               }
             }
-            if (lane < 16) my_attr[h * 16 + lane] = p[0];
+            // att_r[sentence quarter][32*sub + 16*h + lane] straight into the operand of J7 (its last reader, J8 of the
+            // previous cycle, has completed: every warp drained that accumulator)
+            if (lane < 16) put_relay_operand<NPASS>(rb, quarter, sub * 32 + h * 16 + lane, p[0]);
           }
-          __syncwarp();
-          // att_r of this sentence / column quarter as the operand of J7: every lane stages the same 32 values (only the
-          // relay lane's row of the product is used)
-          uint32_t hi[16], lo[16];
-          {
-            float a[32];
-#pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const float4 t4 = reinterpret_cast<const float4*>(my_attr)[q4];
-              a[4*q4] = t4.x; a[4*q4+1] = t4.y; a[4*q4+2] = t4.z; a[4*q4+3] = t4.w;
-            }
-            split_quarter_row(a, hi, lo);
-          }
-          store_quarter_row<NPASS>(lane_addr, AT_HI, AT_LO, sub, hi, lo);     // J4 (the last reader of ATT) has completed
-          tmem_st_wait();
+          fence_async_smem();
           warp_arrive(&bars.t_ready, 1);
-          __syncwarp();
         }
 
-        // ================= J7 (ACC0): s' = relu(att_r @ Wo_relay + b) on the relay lane; operand of J8; relay row of X patched
+        // ================= J7 (ACC0, transposed): s'[sentence sub][feature 32*quarter + lane] = relu(att_r @ Wo_relay + b)
         {
+          const int f = quarter * 32 + lane;
           wait_acc(0);
-          float v[32];
-          tmem_ld32(lane_addr + ACC0 + sub * 32, v);
+          float v = tmem_ld1(lane_addr + ACC0 + sub);
           tmem_ld_wait();
           free_acc(0);
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_r + sub * 32) + q4);
-            v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
-            v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
-            v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
-            v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
+          v = fmaxf(v + __ldg(bias_r + f), 0.f);
+          s_cur[sub][f] = v;
+          if (!last) {
+            // bf16 hi / lo of s'[sub][f], packed in pairs by the even lanes: operand of J8 (J7 has completed) and the words
+            // that warp (quarter = sub, column quarter = quarter) patches into the relay row of X
+            const __nv_bfloat16 hb = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lb = __float2bfloat16_rn(v - __bfloat162float(hb));
+            uint32_t hw = (uint32_t)__bfloat16_as_ushort(hb), lw = (uint32_t)__bfloat16_as_ushort(lb);
+            hw |= __shfl_down_sync(0xffffffffu, hw, 1) << 16;
+            lw |= __shfl_down_sync(0xffffffffu, lw, 1) << 16;
+            if ((lane & 1) == 0) {
+              const uint32_t off = ((uint32_t)f >> 6) * RB_PLANE + sw128_offset((uint32_t)sub, (uint32_t)f & 63u);
+              *reinterpret_cast<uint32_t*>(rb + off) = hw;
+              patch_w[0][sub][quarter][lane >> 1] = hw;
+              if (NPASS == 3) {
+                *reinterpret_cast<uint32_t*>(rb + 2 * RB_PLANE + off) = lw;
+                patch_w[1][sub][quarter][lane >> 1] = lw;
+              }
+            }
+            fence_async_smem();
+            warp_arrive(&bars.t_ready, 1);
           }
-          if (lane == 31) {
-#pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4)
-              reinterpret_cast<float4*>(my_s)[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-            if (last) {
+          compute_warps_sync();                                              // s' of the four sentences is complete
+          DSC_TR(warp ? 512 : 256);
+          if (last) {
+            if (lane == 31) {
               float4* xr = reinterpret_cast<float4*>(Xrow + ((int64_t)t * 128 + row_in_tile) * 128 + sub * 32);
 #pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4) xr[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
+              for (int q4 = 0; q4 < 8; ++q4) xr[q4] = reinterpret_cast<const float4*>(my_s)[q4];
             }
-          }
-          if (!last) {
-            uint32_t hi[16], lo[16];
-            split_quarter_row(v, hi, lo);
-            store_quarter_row<NPASS>(lane_addr, AT_HI, AT_LO, sub, hi, lo);  // operand of J8 (J7 has completed)
-            tmem_st_wait();
-            warp_arrive(&bars.t_ready, 1);
+          } else {
             // patch the relay row of the X operand with s' (J5/J6, the last readers of X', have completed): every lane
             // rewrites its own row unchanged, the relay lane substitutes the new words
-            {
+#pragma unroll
+            for (int part = 0; part < ((NPASS == 3) ? 2 : 1); ++part) {
               uint32_t w[16];
-              tmem_ld16(lane_addr + AX_HI + sub * 16, reinterpret_cast<float*>(w));
+              const uint32_t col = lane_addr + (part ? AX_LO : AX_HI) + sub * 16;
+              tmem_ld16(col, reinterpret_cast<float*>(w));
               tmem_ld_wait();
               if (lane == 31) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) w[i] = hi[i];
-              }
-              tmem_st16(lane_addr + AX_HI + sub * 16, w);
-              if (NPASS == 3) {
-                tmem_ld16(lane_addr + AX_LO + sub * 16, reinterpret_cast<float*>(w));
-                tmem_ld_wait();
-                if (lane == 31) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) w[i] = lo[i];
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  const uint4 pw = reinterpret_cast<const uint4*>(patch_w[part][quarter][sub])[i4];
+                  w[4*i4] = pw.x; w[4*i4+1] = pw.y; w[4*i4+2] = pw.z; w[4*i4+3] = pw.w;
                 }
-                tmem_st16(lane_addr + AX_LO + sub * 16, w);
               }
+              tmem_st16(col, w);
             }
+            DSC_TR(warp ? 512 : 256);
             tmem_st_wait();
             warp_arrive(&bars.x_ready, 1);
             load_kve(gp);                                                // e-keys of the next cycle's first head pair
-            // ================= J8 (ACC1): q' = s' @ Wq_relay on the relay lane
+            // ================= J8 (ACC1, transposed): q'[sentence sub][feature] = s' @ Wq_relay
             wait_acc(1);
-            tmem_ld32(lane_addr + ACC1 + sub * 32, v);
+            v = tmem_ld1(lane_addr + ACC1 + sub);
             tmem_ld_wait();
             free_acc(1);
-            if (lane == 31) {
-#pragma unroll
-              for (int q4 = 0; q4 < 8; ++q4)
-                reinterpret_cast<float4*>(my_q)[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
-            }
-            __syncwarp();
+            q_cur[sub][f] = v;
           }
         }
       }
@@ -513,16 +555,26 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
 
 using namespace dsc;
 
-template <int NPASS>
+static bool g_star_trace_on = false;
+
+template <int NPASS, bool TRACE>
 static int launch_star_fused(const float* xi0, const float* s0, const float* q0, const float* kvei, const float* kv2i, int n2,
                              const sf::Weights& w, const float* bias_o, const float* bias_r, float* xrow, int n_tiles,
                              int n_cycles, cudaStream_t s) {
-  constexpr size_t smem = (size_t)sf::STAGES * sf::STAGE_BYTES + 1024;
-  cudaError_t e = cudaFuncSetAttribute(star_fused_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr size_t smem = (size_t)sf::STAGES * sf::STAGE_BYTES + sf::RB_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(star_fused_kernel<NPASS, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("dsc_star_cycles_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
   const int grid = n_tiles < kSMs ? n_tiles : kSMs;
-  star_fused_kernel<NPASS><<<grid, sf::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles);
+  star_fused_kernel<NPASS, TRACE><<<grid, sf::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles);
   return check_launch("dsc_star_cycles_tc");
+}
+
+extern "C" int dsc_debug_star_trace(void* device_buffer_768_u64) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(device_buffer_768_u64);
+  cudaError_t e = cudaMemcpyToSymbol(dsc::g_star_trace, &p, sizeof(p));
+  if (e != cudaSuccess) { set_error("dsc_debug_star_trace: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
+  g_star_trace_on = p != nullptr;
+  return DSC_OK;
 }
 
 extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, const float* kv_e,
@@ -546,6 +598,11 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
   sf::Weights w{reinterpret_cast<const uint8_t*>(packed_wqkv_grouped), reinterpret_cast<const uint8_t*>(packed_wo),
                 reinterpret_cast<const uint8_t*>(packed_wkv_relay), reinterpret_cast<const uint8_t*>(packed_wo_relay),
                 reinterpret_cast<const uint8_t*>(packed_wq_relay)};
-  return prec == 1 ? launch_star_fused<3>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, as_stream(stream))
-                   : launch_star_fused<1>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_sent / 4, n_cycles, as_stream(stream));
+  cudaStream_t st = as_stream(stream);
+  const int n_tiles = n_sent / 4;
+  if (g_star_trace_on)
+    return prec == 1 ? launch_star_fused<3, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st)
+                     : launch_star_fused<1, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st);
+  return prec == 1 ? launch_star_fused<3, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st)
+                   : launch_star_fused<1, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st);
 }

@@ -319,6 +319,10 @@ int dsc_adam_step(float* param, const float* grad, const float* grad2, float* m,
  * the A operand in tensor memory (ts_mode != 0) or shared memory; result in cycles_dev[0]. */
 int dsc_umma_probe(int ts_mode, int n, int iters, long long* cycles_dev, void* stream);
 
+/* Debug timeline of dsc_star_cycles_tc (not on the product path): registers a device buffer of 768 uint64 (NULL = off);
+ * CTA 0 of every later launch stamps clock64() at the hand-offs of its first tile (layout: dsc_star_fused.cu). */
+int dsc_debug_star_trace(void* device_buffer_768_u64);
+
 #ifdef __cplusplus
 }
 #endif
