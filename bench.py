@@ -235,16 +235,26 @@ def main():
     # star_fused_kernel (dsc_star_cycles_tc): all 8 cycles of a star layer in one launch, tile state in TMEM/smem, so
     # it is bound by the tensor pipe, not HBM.  Algorithmic FLOPs per sentence and cycle:
     #   32 rows x 128 x (384 [Wq|Wk|Wv]_sat + 128 Wo_sat + 256 [Wk|Wv]_relay) x 2  +  2 relay GEMVs x 128 x 128 x 2
+    # (only the FLOPs a launch really executes are counted: see launch_flops)
     # Every fp32-class product costs three bf16 UMMA passes (bf16x3), so `achieved` counts 3 tensor FLOPs per
     # algorithmic FLOP and is compared with the measured bf16 peak (sustained: the kernel is timed inside a long step).
-    FLOPS_PER_SENT_CYCLE = 32 * 128 * (384 + 128 + 256) * 2 + 2 * 128 * 128 * 2
+    SAT_HALF = 32 * 128 * (384 + 128) * 2          # J0..J4 of a cycle, per sentence
+    RELAY_KV = 32 * 128 * 256 * 2                  # J5, J6
+    GEMV = 128 * 128 * 2                           # J7 every cycle, J8 every cycle but the first
+
+    def launch_flops(meta):
+        """Algorithmic FLOPs of one dsc_star_cycles_tc launch; a greedy-step launch skips the satellite half of its
+        first cycle (DSC_STAR_FIRST_SAT_DONE: computed once per batch)."""
+        n_sent, cycles, _n2, first_sat_done = meta
+        per_sent = cycles * (SAT_HALF + RELAY_KV + GEMV) + (cycles - 1) * GEMV - (SAT_HALF if first_sat_done else 0)
+        return float(per_sent) * n_sent
+
     passes = {1: 3, 2: 1}.get(args.prec, 0)
     dom = [(a.elapsed_time(b), meta) for op, a, b, meta in prof if op == "dsc_star_cycles_tc" and meta[0] == S]
     roof = None
     if dom and passes:
         mean_ms = sum(t for t, _ in dom) / len(dom)
-        cycles = dom[0][1][1]
-        flops = float(FLOPS_PER_SENT_CYCLE) * S * cycles
+        flops = sum(launch_flops(m) for _, m in dom) / len(dom)          # mean over the timed launches
         achieved = passes * flops / (mean_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roof = {"bound": "tensor", "kernel": "star_fused_kernel<3> via dsc_star_cycles_tc (8 star cycles per launch: QKV / Wo / relay "

@@ -56,6 +56,17 @@ constexpr int STAGES = 3;
 constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
 constexpr int JOBS = 9;
+constexpr uint32_t ACC_Q = ACC1 + 96;                         // J8's 16 columns: behind the 96 columns of a QKV job
+// Issue order of a cycle: J0..J3, then J8 (the query q' of THIS cycle's relay attention, from the previous cycle's s';
+// absent in cycle 0, whose query is an input), then J4..J7.  J8 sits behind the QKV jobs so that it runs while the
+// compute warps are still busy with the satellite attention, instead of delaying J0.
+// skip0: the satellite phase of cycle 0 (J0..J4) was computed by an earlier launch (it depends on the e tile only, not on
+// the decoded prefix): x_tile0 holds X' and cycle 0 is J5, J6, J7.
+__device__ __forceinline__ int jobs_in_cycle(int c, bool skip0) { return c ? JOBS : (skip0 ? 3 : JOBS - 1); }
+__device__ __forceinline__ int job_at(int c, int i, bool skip0) {
+  if (c == 0) return skip0 ? 5 + i : i;
+  return i < 4 ? i : (i == 4 ? 8 : i - 1);
+}
 constexpr uint32_t RB_PLANE = 16 * 128;                       // relay-vector operand: one (part, kb) plane = 16 rows x 128 B
 constexpr uint32_t RB_BYTES = 4 * RB_PLANE;                   // 8 KB behind the ring
 
@@ -63,6 +74,7 @@ struct Bars {
   uint64_t w_full[STAGES], w_free[STAGES];
   uint64_t acc_full[2], acc_free[2];
   uint64_t x_ready, t_ready;
+  uint64_t q_full;                          // the relay query q' (J8) is in its accumulator columns
 };
 struct Weights {
   const uint8_t* qkv;    // grouped [Wq|Wk|Wv]_sat, 384 rows
@@ -154,8 +166,9 @@ __global__ void __launch_bounds__(sf::kThreads, 1)
 star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, const float* __restrict__ Q0,
                   const float* __restrict__ KVEI, const float* __restrict__ KV2I, int n2, sf::Weights W,
                   const float* __restrict__ bias_o, const float* __restrict__ bias_r,
-                  float* __restrict__ Xrow, int n_tiles, int n_cycles) {
+                  float* __restrict__ Xrow, int n_tiles, int n_cycles, int skip0_i) {
   using namespace sf;
+  const bool skip0 = skip0_i != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* rb = ring + STAGES * STAGE_BYTES;         // att_r, then s': B operand of the transposed relay GEMVs (rows 4..15 zero)
@@ -177,6 +190,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kArrivals); }
     mbar_init(&bars.x_ready, kArrivals);
     mbar_init(&bars.t_ready, kArrivals);
+    mbar_init(&bars.q_full, 1);
     fence_barrier_init();
   }
   if (warp == sf::kMmaWarp) tmem_alloc<512>(&tmem_base_s);
@@ -192,8 +206,9 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
       uint32_t n = 0;                                   // chunks issued so far
       for (int t = 0; t < my_tiles; ++t)
         for (int c = 0; c < n_cycles; ++c) {
-          const int jobs = (c + 1 == n_cycles) ? JOBS - 1 : JOBS;      // the last cycle needs no next query
-          for (int j = 0; j < jobs; ++j, ++n) {
+          const int jobs = jobs_in_cycle(c, skip0);
+          for (int ji = 0; ji < jobs; ++ji, ++n) {
+            const int j = job_at(c, ji, skip0);
             const uint32_t st = n % STAGES;
             mbar_wait(&bars.w_free[st], ((n / STAGES) - 1) & 1);
             const uint8_t* blob; uint32_t rows, row0, n_pad;
@@ -217,14 +232,17 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
       uint32_t n = 0, use0 = 0, use1 = 0, xr = 0, tr = 0;  // chunks consumed, accumulator uses, operand phases consumed
       for (int t = 0; t < my_tiles; ++t)
         for (int c = 0; c < n_cycles; ++c) {
-          const int jobs = (c + 1 == n_cycles) ? JOBS - 1 : JOBS;
-          for (int j = 0; j < jobs; ++j, ++n) {
-            const uint32_t st = n % STAGES, b = (j < 7) ? ((uint32_t)j & 1u) : (uint32_t)(j - 7);   // J7 -> ACC0, J8 -> ACC1
+          const int jobs = jobs_in_cycle(c, skip0);
+          for (int ji = 0; ji < jobs; ++ji, ++n) {
+            const int j = job_at(c, ji, skip0);
+            const uint32_t st = n % STAGES, b = (j < 7) ? ((uint32_t)j & 1u) : 0u;                    // J7 -> ACC0
             if (j == 0 || j == 5) { mbar_wait(&bars.x_ready, xr & 1); ++xr; }          // X staged / X' restaged
             if (j == 4 || j == 7 || j == 8) { mbar_wait(&bars.t_ready, tr & 1); ++tr; } // ATT / att_r / s' staged
             mbar_wait(&bars.w_full[st], (n / STAGES) & 1);
-            if (b) { mbar_wait(&bars.acc_free[1], (use1 - 1) & 1); ++use1; }
-            else   { mbar_wait(&bars.acc_free[0], (use0 - 1) & 1); ++use0; }
+            if (j != 8) {                                                              // J8 has its own columns (ACC_Q); every
+              if (b) { mbar_wait(&bars.acc_free[1], (use1 - 1) & 1); ++use1; }         // warp read the previous q' before it
+              else   { mbar_wait(&bars.acc_free[0], (use0 - 1) & 1); ++use0; }         // freed this cycle's first accumulators
+            }
             tc_fence_after();
             if (t == 0) DSC_TR(0);
             const uint32_t bb = ring_base + st * STAGE_BYTES;
@@ -232,10 +250,11 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             if (leader) {
               if (j < 4) issue_group<NPASS, 96>(tmem_base, acc, AX_HI, AX_LO, bb, 96u * 128u, 0u);
               else if (j == 4) issue_group<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0u);
-              else if (j >= 7) issue_relay_gemv<NPASS>(tmem_base + acc, bb, rb_base);
+              else if (j == 7) issue_relay_gemv<NPASS>(tmem_base + acc, bb, rb_base);
+              else if (j == 8) issue_relay_gemv<NPASS>(tmem_base + ACC_Q, bb, rb_base);
               else issue_group<NPASS, 128>(tmem_base, acc, AX_HI, AX_LO, bb, 128u * 128u, 0u);
               umma_commit(&bars.w_free[st]);
-              umma_commit(&bars.acc_full[b]);
+              umma_commit(j == 8 ? &bars.q_full : &bars.acc_full[b]);
             }
             if (t == 0) DSC_TR(0);
             __syncwarp();
@@ -300,10 +319,11 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
         tmem_st_wait();
         warp_arrive(&bars.x_ready, 1);
       }
-      load_kve(gp);
+      if (!skip0) load_kve(gp);
 
       for (int c = 0; c < n_cycles; ++c) {
         const bool last = (c + 1 == n_cycles);
+        if (!(skip0 && c == 0)) {
         // ================= J0..J3: this warp takes head pairs g = gp and gp + 2 (accumulator gp), head 2g + hh
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
@@ -311,11 +331,16 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           wait_acc(gp);
           const uint32_t col = lane_addr + (gp ? ACC1 : ACC0) + hh * 16;
           float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f, l4 = 0.f;
+          float v[16];
           {
+            // q, k, v of (row, head) to registers in one go, then the accumulator goes straight back to the issuer: holding
+            // it through the logits and the softmax (0.75 us, longer than a QKV UMMA) serialised J2 / J3 behind J0 / J1
             float q[16], k[16];
             tmem_ld16(col, q);
             tmem_ld16(col + 32, k);
+            tmem_ld16(col + 64, v);
             tmem_ld_wait();
+            warp_arrive(&bars.acc_free[gp], 2);                     // 8 of the 16 warps drain a QKV accumulator
 #pragma unroll
             for (int d = 0; d < 16; ++d) {
               const float ku = __shfl_sync(0xffffffffu, k[d], up);
@@ -328,15 +353,11 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
               l4 = fmaf(q[d], ks, l4);
             }
           }
-          float v[16];
-          tmem_ld16(col + 64, v);
           l0 *= 0.25f; l1 *= 0.25f; l2 *= 0.25f; l3 *= 0.25f; l4 *= 0.25f;
           const float mx = fmaxf(fmaxf(fmaxf(l0, l1), fmaxf(l2, l3)), l4);
           l0 = expf(l0 - mx); l1 = expf(l1 - mx); l2 = expf(l2 - mx); l3 = expf(l3 - mx); l4 = expf(l4 - mx);
           const float inv = 1.0f / (l0 + l1 + l2 + l3 + l4);
           l0 *= inv; l1 *= inv; l2 *= inv; l3 *= inv; l4 *= inv;
-          tmem_ld_wait();
-          warp_arrive(&bars.acc_free[gp], 2);                       // 8 of the 16 warps drain a QKV accumulator
           uint32_t ohi[8], olo[8];
 #pragma unroll
           for (int d2 = 0; d2 < 8; ++d2) {
@@ -364,6 +385,14 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
         if (gp) use0 += 2; else use1 += 2;                          // the two QKV jobs drained by the other warps
         tmem_st_wait();
         warp_arrive(&bars.t_ready, 1);
+        if (c > 0) {
+          // J8 (transposed, issued behind J3): q'[sentence sub][feature 32*quarter + lane] = s' @ Wq_relay
+          mbar_wait(&bars.q_full, (uint32_t)(c - 1 + ti * (n_cycles - 1)) & 1u);
+          tc_fence_after();
+          const float qv = tmem_ld1(lane_addr + ACC_Q + sub);
+          tmem_ld_wait();
+          q_cur[sub][quarter * 32 + lane] = qv;                      // read after the barrier at the head of the J5 block
+        }
 
         // ================= J4: X' = relu(ATT @ Wo + b), columns 32*sub..; the relay row keeps s; re-staged as X
         {
@@ -399,6 +428,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           tmem_st_wait();
           warp_arrive(&bars.x_ready, 1);
         }
+        }   // !(skip0 && c == 0)
 
         // ================= J5 (K -> ACC1), J6 (V -> ACC0): relay attention, heads 2*sub and 2*sub+1, lane = key row
         {
@@ -535,12 +565,6 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             tmem_st_wait();
             warp_arrive(&bars.x_ready, 1);
             load_kve(gp);                                                // e-keys of the next cycle's first head pair
-            // ================= J8 (ACC1, transposed): q'[sentence sub][feature] = s' @ Wq_relay
-            wait_acc(1);
-            v = tmem_ld1(lane_addr + ACC1 + sub);
-            tmem_ld_wait();
-            free_acc(1);
-            q_cur[sub][f] = v;
           }
         }
       }
@@ -560,12 +584,12 @@ static bool g_star_trace_on = false;
 template <int NPASS, bool TRACE>
 static int launch_star_fused(const float* xi0, const float* s0, const float* q0, const float* kvei, const float* kv2i, int n2,
                              const sf::Weights& w, const float* bias_o, const float* bias_r, float* xrow, int n_tiles,
-                             int n_cycles, cudaStream_t s) {
+                             int n_cycles, int skip0, cudaStream_t s) {
   constexpr size_t smem = (size_t)sf::STAGES * sf::STAGE_BYTES + sf::RB_BYTES + 1024;
   cudaError_t e = cudaFuncSetAttribute(star_fused_kernel<NPASS, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("dsc_star_cycles_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
   const int grid = n_tiles < kSMs ? n_tiles : kSMs;
-  star_fused_kernel<NPASS, TRACE><<<grid, sf::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles);
+  star_fused_kernel<NPASS, TRACE><<<grid, sf::kThreads, smem, s>>>(xi0, s0, q0, kvei, kv2i, n2, w, bias_o, bias_r, xrow, n_tiles, n_cycles, skip0);
   return check_launch("dsc_star_cycles_tc");
 }
 
@@ -591,8 +615,10 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
               aligned16(bias_o) && aligned16(bias_o_relay) && aligned16(x_rowmajor), "dsc_star_cycles_tc: misaligned pointer");
   DSC_REQUIRE((((uintptr_t)packed_wqkv_grouped | (uintptr_t)packed_wo | (uintptr_t)packed_wkv_relay | (uintptr_t)packed_wo_relay |
                 (uintptr_t)packed_wq_relay) & 127u) == 0, "dsc_star_cycles_tc: packed weights must be 128-byte aligned");
+  const int skip0 = (prec & DSC_STAR_FIRST_SAT_DONE) ? 1 : 0;
   prec &= 255;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_cycles_tc: prec must be 1 (bf16x3) or 2 (bf16)");
+  DSC_REQUIRE(!skip0 || n_cycles >= 2, "dsc_star_cycles_tc: DSC_STAR_FIRST_SAT_DONE needs n_cycles >= 2");
   if (n_sent == 0) return DSC_OK;
   if (n2 == 0) kv2 = kv_e;        // rows are read but masked (lane < n2 is false): any readable [n_sent][64][32][4] floats do
   sf::Weights w{reinterpret_cast<const uint8_t*>(packed_wqkv_grouped), reinterpret_cast<const uint8_t*>(packed_wo),
@@ -601,8 +627,8 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
   cudaStream_t st = as_stream(stream);
   const int n_tiles = n_sent / 4;
   if (g_star_trace_on)
-    return prec == 1 ? launch_star_fused<3, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st)
-                     : launch_star_fused<1, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st);
-  return prec == 1 ? launch_star_fused<3, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st)
-                   : launch_star_fused<1, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, st);
+    return prec == 1 ? launch_star_fused<3, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st)
+                     : launch_star_fused<1, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st);
+  return prec == 1 ? launch_star_fused<3, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st)
+                   : launch_star_fused<1, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st);
 }

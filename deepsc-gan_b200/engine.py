@@ -99,7 +99,7 @@ class StarGreedyDecoder:
         mem = net.channel_decoder.call(received)                      # hoisted out of the step loop
         st0 = self.layers[0]
         _lib.star_pack(mem.contiguous(), st0.tile)
-        prepare_kv_e(st0.tile, st0.layer.multi_att_satellite, st0.ws, st0.relay)
+        prepare_kv_e(st0.tile, st0.layer.multi_att_satellite, st0.ws, st0.relay, first_sat=True)
         tc = use_tc(S)
         self.outputs.zero_()
         self.outputs[:, 0] = start_idx

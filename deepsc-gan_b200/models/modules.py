@@ -276,6 +276,7 @@ class StarWorkspace:
         self.kv2i = None                                    # interleaved h2 cache built from a row-major kv2
         self.xi0 = None                                     # interleaved e tile, s0 and q0 = s0 @ wq_relay: the
         self.s0 = self.q0 = None                            # cycle-0 state of the one-launch kernel (constant per e tile)
+        self.xi1 = self.xi1_buf = None                      # interleaved X' of cycle 0 (satellite half precomputed, greedy decode)
 
     def tc_buffers(self):
         if self.kvei is None:
@@ -288,9 +289,12 @@ def use_tc(n_sent: int) -> bool:
     return PREC != 0 and n_sent % 4 == 0
 
 
-def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace, relay: Optional[sublayer1] = None) -> None:
+def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace, relay: Optional[sublayer1] = None,
+                 first_sat: bool = False) -> None:
     """Everything that depends on the e tile only (constant over cycles and greedy steps): k|v of the e rows under the
-    satellite weights and, for the one-launch tcgen05 kernel, the interleaved e tile, s0 and q0 = s0 @ wq_relay."""
+    satellite weights and, for the one-launch tcgen05 kernel, the interleaved e tile, s0 and q0 = s0 @ wq_relay.
+    ``first_sat``: also the satellite half of the FIRST cycle (models/modules.py:287-300 reads h = e, s = mean(e) and
+    the e keys only), so that a greedy decoder runs it once per batch instead of once per step."""
     S = e_tile.shape[0]
     _lib.linear(e_tile.view(S * 32, 128), sat._packed("kv"), None, out=ws.kv_e, prec=PREC)
     if use_tc(S):
@@ -302,6 +306,16 @@ def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace, relay:
             _lib.star_interleave(e_tile.view(S // 4, 128, 128), ws.xi0, 128)
             ws.s0.copy_(e_tile[:, 31, :])
             _lib.linear(ws.s0, relay.wq.kernel.detach(), None, out=ws.q0, prec=PREC)
+            ws.xi1 = None
+            if first_sat:
+                # one cycle without target keys: rows 0..30 of the result are X' = relu(ATT @ Wo + b) of cycle 0
+                _lib.star_cycles_tc(ws.xi0, ws.s0, ws.q0, ws.kvei, None, 0, sat._packed("qkv_grouped"),
+                                    sat.dense.kernel.detach(), relay._packed("kv"), relay.dense.kernel.detach(),
+                                    relay.wq.kernel.detach(), sat.dense.bias.detach(), relay.dense.bias.detach(),
+                                    ws.x, S, 1, PREC)
+                if ws.xi1_buf is None:
+                    ws.xi1_buf = torch.empty((S * 4096,), **f)
+                ws.xi1 = _lib.star_interleave(ws.x.view(S // 4, 128, 128), ws.xi1_buf, 128)
 
 
 def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_num: int,
@@ -325,10 +339,11 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
             pad = torch.zeros((S, 32, 256), device=e_tile.device, dtype=torch.float32)
             pad[:, : kv2.shape[1]] = kv2
             kv2i = _lib.star_interleave(pad, torch.empty_like(pad).view(-1), 32)
-        return _lib.star_cycles_tc(ws.xi0, ws.s0, ws.q0, ws.kvei, kv2i, n2, sat._packed("qkv_grouped"),
+        skip = kv_e_ready and ws.xi1 is not None and cycle_num >= 2
+        return _lib.star_cycles_tc(ws.xi1 if skip else ws.xi0, ws.s0, ws.q0, ws.kvei, kv2i, n2, sat._packed("qkv_grouped"),
                                    sat.dense.kernel.detach(), relay._packed("kv"), relay.dense.kernel.detach(),
                                    relay.wq.kernel.detach(), sat.dense.bias.detach(), relay.dense.bias.detach(),
-                                   ws.x, S, cycle_num, PREC)
+                                   ws.x, S, cycle_num, PREC | (_lib.STAR_FIRST_SAT_DONE if skip else 0))
     if use_tc(S):
         # tcgen05 path: two fused persistent kernels per cycle (projection + satellite attention; dense + relay
         # k|v projection + relay attention) plus the two per-sentence Dense calls of the relay node.

@@ -126,7 +126,11 @@ int dsc_star_mix_tc(const float* att, float* x_tile, float* x_rowmajor, const fl
  * q0 [n_sent,128] = s0 @ wq_relay; kv_e, kv2, n2 as in dsc_star_sat_tc / dsc_star_mix_tc; the five packed weights are
  * dsc_pack_weight images of the grouped [128,384] satellite projection, wo_satellite, [wk|wv]_relay, wo_relay, wq_relay
  * (pass the satellite matrices again for the layers that drive the relay with the satellite weights, :175, :243).
- * x_rowmajor [n_sent][32][128] receives the tile after n_cycles cycles (rows 0..30 = h, row 31 = s). */
+ * x_rowmajor [n_sent][32][128] receives the tile after n_cycles cycles (rows 0..30 = h, row 31 = s).
+ * prec | DSC_STAR_FIRST_SAT_DONE: the satellite half of the FIRST cycle (:287-300) - which depends on the e tile only,
+ * not on kv2 - was computed before (rows 0..30 of a 1-cycle call's output, re-interleaved): x_tile0 holds that X' and
+ * the first cycle runs its relay half only.  A greedy decoder pays the satellite half once per batch, not per step. */
+#define DSC_STAR_FIRST_SAT_DONE 0x100
 int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, const float* kv_e,
                        const float* kv2, int n2,
                        const void* packed_wqkv_grouped, const void* packed_wo, const void* packed_wkv_relay,

@@ -140,6 +140,27 @@ def test_star_cycle_kernels_match_literal_oracle(L, dev, n2, prec, tol, monkeypa
     assert rel_err(x3[:, :31], h_ref3) < 4 * tol and rel_err(x3[:, 31], s_ref3) < 4 * tol
 
 
+@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("S,n2", [(8, 0), (12, 17), (600, 30)])
+def test_star_cycles_first_satellite_half_cached(L, dev, S, n2, prec, monkeypatch):
+    """DSC_STAR_FIRST_SAT_DONE (the greedy decoder's once-per-batch satellite half of cycle 0) gives bit-identical
+    tiles to the plain call: same products, same order."""
+    import deepsc_gan_b200.models.modules as M
+    monkeypatch.setattr(M, "PREC", prec)
+    torch.manual_seed(3)
+    sat, relay = M.sublayer1(128, 8).to(dev), M.sublayer1(128, 8).to(dev)
+    tile = L.star_pack(torch.randn(S, 31, 128, device=dev))
+    kv2 = torch.randn(S, 30, 256, device=dev) if n2 else None
+    ws = M.StarWorkspace(S, dev)
+    M.prepare_kv_e(tile, sat, ws, relay)
+    plain = M.star_cycles(tile, sat, relay, 3, kv2, n2, ws, kv_e_ready=True).clone()
+    M.prepare_kv_e(tile, sat, ws, relay, first_sat=True)
+    assert ws.xi1 is not None
+    cached = M.star_cycles(tile, sat, relay, 3, kv2, n2, ws, kv_e_ready=True)
+    torch.cuda.synchronize()
+    assert torch.equal(plain, cached)
+
+
 @pytest.mark.parametrize("lq,lk,mode", [(31, 31, "pad"), (30, 30, "combined"), (1, 17, "ids"), (30, 31, "pad"), (7, 7, "none")])
 def test_mha_attention_matches_oracle(L, dev, lq, lk, mode):
     g = torch.Generator().manual_seed(lq * 100 + lk)

@@ -44,14 +44,13 @@ print(f"prec={prec} n2={n2} cycles={cycles}; times in us from the first stamp (a
 print("issuer: job, ready-to-issue, issued")
 n = 0
 for c in range(cycles):
-    jobs = 8 if c + 1 == cycles else 9
-    for j in range(jobs):
+    for j in ([0, 1, 2, 3] + ([8] if c else []) + [4, 5, 6, 7]):      # issue order: J8 (this cycle's relay query) behind J3
         print(f"  c{c} J{j}: ready {us(iss[2*n]):8.2f}  issued {us(iss[2*n+1]):8.2f}")
         n += 1
 names0 = ["x_ready(tile)"]
 per0 = ["J0 acc seen", "J0 acc freed", "J2 acc seen", "J2 acc freed", "ATT staged (t_ready)", "J4 acc seen", "J4 acc freed",
         "X' staged (x_ready)", "J5 acc seen", "J5 freed", "J6 acc seen", "J6 freed", "att_r staged (t_ready)", "J7 acc seen",
-        "J7 freed", "s' staged (t_ready)", "s' barrier passed", "relay lane split", "X patched (x_ready)", "J8 acc seen", "J8 freed"]
+        "J7 freed", "s' staged (t_ready)", "s' barrier passed", "relay row patched", "X patched (x_ready)"]
 print("compute warp 0:")
 i = 0
 print(f"  {names0[0]:28s} {us(w0[i]):8.2f}"); i += 1
