@@ -28,25 +28,30 @@ bleu_counts_kernel(const int32_t* __restrict__ ref, int ref_len, const int32_t* 
   int* h = hs[warp];
   const int rl = clean_into(ref + (int64_t)s * ref_len, ref_len, lane, r);
   const int hl = clean_into(hyp + (int64_t)s * hyp_len, hyp_len, lane, h);
+  // Lane i owns hypothesis position i.  eq_h / eq_r: bit j set when hyp[j] / ref[j] equals hyp[i] (one pass over the
+  // cleaned sentences, shared-memory broadcasts).  An n-gram match at (i, j) is the AND of the unigram masks of
+  // positions i..i+n-1 shifted by 0..n-1, so every order costs one shuffle, one shift and one AND per side instead of
+  // an O(31 * n) compare loop; counts, clipping and the first-occurrence rule are popcounts of those masks.
+  const int mine = (lane < hl) ? h[lane] : -1;
+  unsigned eq_h = 0, eq_r = 0;
+  for (int j = 0; j < hl; ++j) eq_h |= (unsigned)(h[j] == mine) << j;
+  for (int j = 0; j < rl; ++j) eq_r |= (unsigned)(r[j] == mine) << j;
+  unsigned mh = eq_h, mr = eq_r;                   // n-gram masks of the current order
   int out_match[4], out_total[4];
 #pragma unroll
   for (int g = 1; g <= 4; ++g) {
     const int nh = hl - g + 1, nr = rl - g + 1;     // number of n-grams (may be <= 0)
+    if (g > 1) {
+      // lane i + g - 1 holds the unigram masks of the n-gram's last token (lanes past the end read garbage: masked below)
+      mh &= __shfl_down_sync(0xffffffffu, eq_h, g - 1) >> (g - 1);
+      mr &= __shfl_down_sync(0xffffffffu, eq_r, g - 1) >> (g - 1);
+    }
     int contrib = 0;
     if (lane < nh) {
-      bool first = true;
-      int ch = 0, cr = 0;
-      for (int j = 0; j < nh; ++j) {
-        bool eq = true;
-        for (int t = 0; t < g; ++t) eq = eq && (h[j + t] == h[lane + t]);
-        if (eq) { ++ch; if (j < lane) first = false; }
-      }
-      for (int j = 0; j < nr; ++j) {
-        bool eq = true;
-        for (int t = 0; t < g; ++t) eq = eq && (r[j + t] == h[lane + t]);
-        if (eq) ++cr;
-      }
-      if (first) contrib = min(ch, cr);
+      const unsigned vh = mh & ((nh >= 32) ? 0xffffffffu : ((1u << nh) - 1u));
+      const unsigned vr = (nr > 0) ? (mr & ((nr >= 32) ? 0xffffffffu : ((1u << nr) - 1u))) : 0u;
+      const bool first = (vh & ((1u << lane) - 1u)) == 0u;          // no earlier occurrence of this n-gram in hyp
+      if (first) contrib = min(__popc(vh), __popc(vr));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);

@@ -21,13 +21,15 @@ struct Philox {
     }
     return make_uint4(c0, c1, c2, c3);
   }
+  // Box-Muller on the SFU: lg2 / rsqrt / sin / cos approximations (absolute error < 4e-6 on a unit normal, far inside the
+  // 1e-3 budget of the channel symbols); the exact libm forms made the kernel instruction-bound at 41 % of HBM.
   static __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-    float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;     // (0, 1]
-    float u2 = (float)b * 2.3283064365386963e-10f;              // [0, 1]
-    float r = sqrtf(-2.0f * logf(u1));
+    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;     // (0, 1]
+    const float t = (float)b * 2.3283064365386963e-10f - 0.5f;        // [-0.5, 0.5]: angle 2*pi*t + pi
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));        // sqrt(-2 ln u1)
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
-    return make_float2(r * c, r * s);
+    __sincosf(6.283185307179586f * t, &s, &c);
+    return make_float2(-r * c, -r * s);                                 // cos(a + pi) = -cos a, sin(a + pi) = -sin a
   }
 };
 
@@ -37,51 +39,71 @@ channel_kernel(const float4* __restrict__ x, const float* __restrict__ x_sumsq, 
                const float4* __restrict__ p, const float* __restrict__ p_sumsq, float p_factor,
                const float* __restrict__ p_scale, const float2* __restrict__ h,
                const float* __restrict__ n_std, int detector,
-               float4* __restrict__ y, float4* __restrict__ x_norm, int64_t n4, int64_t unit4) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int u = (int)(i / unit4);
-    const float elems = (float)(unit4 * 4);
-    float4 v = ld_stream(x + i);
-    if (x_sumsq != nullptr) {
-      float sc = 1.0f / sqrtf(x_factor * __ldg(x_sumsq + u) / elems);
-      v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+               float4* __restrict__ y, float4* __restrict__ x_norm, int n_units, int unit4) {
+  // grid (chunks, units): the per-unit scalars are loaded once per CTA and unit, no index division in the stream loop
+  for (int u = blockIdx.y; u < n_units; u += gridDim.y) {
+    const float elems = (float)unit4 * 4.0f;
+    const float sc = x_sumsq ? 1.0f / sqrtf(x_factor * __ldg(x_sumsq + u) / elems) : 1.0f;
+    const float ns = y ? __ldg(n_std + u) : 0.f;
+    float ps = 0.f;
+    if (p != nullptr) {
+      ps = p_scale ? __ldg(p_scale + u) : 1.0f;
+      if (p_sumsq != nullptr) ps *= 1.0f / sqrtf(p_factor * __ldg(p_sumsq + u) / elems);
     }
-    if (x_norm != nullptr) x_norm[i] = v;
-    if (y == nullptr) continue;                 // dsc_power_normalize: normalise only
-    float4 z;
-    if (noise != nullptr) {
-      z = ld_stream(noise + i);
-    } else {
-      uint4 r = Philox::gen((uint64_t)i, offset, seed);
-      float2 a = Philox::box_muller(r.x, r.y), b = Philox::box_muller(r.z, r.w);
-      z = make_float4(a.x, a.y, b.x, b.y);
+    float2 hh = make_float2(1.f, 0.f);
+    float inv_den = 1.f;
+    if (h != nullptr) {
+      hh = __ldg(h + u);
+      float den = hh.x * hh.x + hh.y * hh.y;
+      if (detector == 2) den += ns * ns * 2.0f;
+      inv_den = 1.0f / den;
     }
-    const float ns = __ldg(n_std + u);
-    float4 o;
-    if (h == nullptr) {
-      o = make_float4(v.x + ns * z.x, v.y + ns * z.y, v.z + ns * z.z, v.w + ns * z.w);
-      if (p != nullptr) {
-        float4 pp = ld_stream(p + i);
-        float ps = p_scale ? __ldg(p_scale + u) : 1.0f;
-        if (p_sumsq != nullptr) ps *= 1.0f / sqrtf(p_factor * __ldg(p_sumsq + u) / elems);
-        o.x = fmaf(ps, pp.x, o.x); o.y = fmaf(ps, pp.y, o.y); o.z = fmaf(ps, pp.z, o.z); o.w = fmaf(ps, pp.w, o.w);
+    const int64_t base = (int64_t)u * unit4;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < unit4; j += gridDim.x * blockDim.x) {
+      const int64_t i = base + j;
+      float4 v = ld_stream(x + i);
+      if (x_sumsq != nullptr) { v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; }
+      if (x_norm != nullptr) x_norm[i] = v;
+      if (y == nullptr) continue;                 // dsc_power_normalize: normalise only
+      float4 z;
+      if (noise != nullptr) {
+        z = ld_stream(noise + i);
+      } else {
+        uint4 r = Philox::gen((uint64_t)i, offset, seed);
+        float2 a = Philox::box_muller(r.x, r.y), b = Philox::box_muller(r.z, r.w);
+        z = make_float4(a.x, a.y, b.x, b.y);
       }
-    } else {
-      const float2 hh = __ldg(h + u);
-      // y = x*h + n  (two complex symbols: (x,y) and (z,w))
-      float yr0 = v.x * hh.x - v.y * hh.y + ns * z.x, yi0 = v.x * hh.y + v.y * hh.x + ns * z.y;
-      float yr1 = v.z * hh.x - v.w * hh.y + ns * z.z, yi1 = v.z * hh.y + v.w * hh.x + ns * z.w;
-      if (detector != 0) {
-        float den = hh.x * hh.x + hh.y * hh.y;
-        if (detector == 2) den += ns * ns * 2.0f;
-        float er0 = (yr0 * hh.x + yi0 * hh.y) / den, ei0 = (yi0 * hh.x - yr0 * hh.y) / den;
-        float er1 = (yr1 * hh.x + yi1 * hh.y) / den, ei1 = (yi1 * hh.x - yr1 * hh.y) / den;
-        yr0 = er0; yi0 = ei0; yr1 = er1; yi1 = ei1;
+      float4 o;
+      if (h == nullptr) {
+        o = make_float4(v.x + ns * z.x, v.y + ns * z.y, v.z + ns * z.z, v.w + ns * z.w);
+        if (p != nullptr) {
+          float4 pp = ld_stream(p + i);
+          o.x = fmaf(ps, pp.x, o.x); o.y = fmaf(ps, pp.y, o.y); o.z = fmaf(ps, pp.z, o.z); o.w = fmaf(ps, pp.w, o.w);
+        }
+      } else {
+        // y = x*h + n  (two complex symbols: (x,y) and (z,w))
+        float yr0 = v.x * hh.x - v.y * hh.y + ns * z.x, yi0 = v.x * hh.y + v.y * hh.x + ns * z.y;
+        float yr1 = v.z * hh.x - v.w * hh.y + ns * z.z, yi1 = v.z * hh.y + v.w * hh.x + ns * z.w;
+        if (detector != 0) {
+          float er0 = (yr0 * hh.x + yi0 * hh.y) * inv_den, ei0 = (yi0 * hh.x - yr0 * hh.y) * inv_den;
+          float er1 = (yr1 * hh.x + yi1 * hh.y) * inv_den, ei1 = (yi1 * hh.x - yr1 * hh.y) * inv_den;
+          yr0 = er0; yi0 = ei0; yr1 = er1; yi1 = ei1;
+        }
+        o = make_float4(yr0, yi0, yr1, yi1);
       }
-      o = make_float4(yr0, yi0, yr1, yi1);
+      st_stream(y + i, o);
     }
-    st_stream(y + i, o);
   }
+}
+
+// grid for n_units units of unit4 float4 each: ~8 CTAs of 256 threads per SM in total, at least one chunk per unit
+static inline dim3 channel_grid(int n_units, int64_t unit4) {
+  int64_t per_unit = (unit4 + 255) / 256;
+  int64_t want_x = ((int64_t)kSMs * 8 + n_units - 1) / n_units;
+  int gx = (int)(per_unit < want_x ? per_unit : want_x);
+  if (gx < 1) gx = 1;
+  int gy = n_units < 65535 ? n_units : 65535;
+  return dim3(gx, gy);
 }
 
 }  // namespace dsc
@@ -94,32 +116,29 @@ extern "C" int dsc_channel(const float* x, const float* x_sumsq, float x_factor,
                            const float* h, const float* n_std, int detector,
                            float* y, float* x_norm, int n_units, int64_t elems_per_unit, void* stream) {
   DSC_REQUIRE(x && y && n_std, "dsc_channel: x, y and n_std are required");
-  DSC_REQUIRE(n_units >= 0 && elems_per_unit > 0 && (elems_per_unit & 3) == 0, "dsc_channel: elems_per_unit must be a positive multiple of 4");
+  DSC_REQUIRE(n_units >= 0 && elems_per_unit > 0 && (elems_per_unit & 3) == 0 && elems_per_unit < ((int64_t)1 << 32),
+              "dsc_channel: elems_per_unit must be a positive multiple of 4 below 2^32");
   DSC_REQUIRE(aligned16(x) && aligned16(y) && (!noise || aligned16(noise)) && (!p || aligned16(p)) && (!x_norm || aligned16(x_norm)),
               "dsc_channel: tensors must be 16-byte aligned");
   if (detector < 0 || detector > 2) { set_error("detector must in LS and MMSE"); return DSC_ERR_BAD_ARG; }
   if (n_units == 0) return DSC_OK;
-  int64_t unit4 = elems_per_unit / 4, n4 = unit4 * n_units;
-  int64_t want = (n4 + 255) / 256;
-  int blocks = (int)(want < (int64_t)kSMs * 8 ? want : (int64_t)kSMs * 8);
-  channel_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+  const int64_t unit4 = elems_per_unit / 4;
+  channel_kernel<<<channel_grid(n_units, unit4), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), x_sumsq, x_factor, reinterpret_cast<const float4*>(noise), seed, offset,
       reinterpret_cast<const float4*>(p), p_sumsq, p_factor, p_scale, reinterpret_cast<const float2*>(h), n_std,
-      detector, reinterpret_cast<float4*>(y), reinterpret_cast<float4*>(x_norm), n4, unit4);
+      detector, reinterpret_cast<float4*>(y), reinterpret_cast<float4*>(x_norm), n_units, (int)unit4);
   return check_launch("dsc_channel");
 }
 
 extern "C" int dsc_power_normalize(const float* x, const float* sumsq, float factor, float* out,
                                    int n_units, int64_t elems_per_unit, void* stream) {
   DSC_REQUIRE(x && sumsq && out, "dsc_power_normalize: null pointer");
-  DSC_REQUIRE(n_units >= 0 && elems_per_unit > 0 && (elems_per_unit & 3) == 0 && aligned16(x) && aligned16(out),
-              "dsc_power_normalize: bad sizes or alignment");
+  DSC_REQUIRE(n_units >= 0 && elems_per_unit > 0 && (elems_per_unit & 3) == 0 && elems_per_unit < ((int64_t)1 << 32) &&
+              aligned16(x) && aligned16(out), "dsc_power_normalize: bad sizes or alignment");
   if (n_units == 0) return DSC_OK;
-  int64_t unit4 = elems_per_unit / 4, n4 = unit4 * n_units;
-  int64_t want = (n4 + 255) / 256;
-  int blocks = (int)(want < (int64_t)kSMs * 8 ? want : (int64_t)kSMs * 8);
-  channel_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+  const int64_t unit4 = elems_per_unit / 4;
+  channel_kernel<<<channel_grid(n_units, unit4), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), sumsq, factor, nullptr, 0, 0, nullptr, nullptr, 1.f, nullptr, nullptr,
-      sumsq /* unused */, 0, nullptr, reinterpret_cast<float4*>(out), n4, unit4);
+      sumsq /* unused */, 0, nullptr, reinterpret_cast<float4*>(out), n_units, (int)unit4);
   return check_launch("dsc_power_normalize");
 }

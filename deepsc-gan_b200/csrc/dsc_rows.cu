@@ -92,11 +92,23 @@ unit_sumsq_kernel(const float* __restrict__ x, float* __restrict__ sumsq, int64_
   const int u = blockIdx.y;
   const float4* p = reinterpret_cast<const float4*>(x + (int64_t)u * elems_per_unit);
   const int64_t n4 = elems_per_unit >> 2;
-  float acc = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = ld_stream(p + i);
-    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  // four independent 16-byte loads in flight per thread; a CTA owns one contiguous chunk of the unit
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 v0 = ld_stream(p + i), v1 = ld_stream(p + i + stride), v2 = ld_stream(p + i + 2 * stride),
+                 v3 = ld_stream(p + i + 3 * stride);
+    a0 += v0.x * v0.x + v0.y * v0.y + v0.z * v0.z + v0.w * v0.w;
+    a1 += v1.x * v1.x + v1.y * v1.y + v1.z * v1.z + v1.w * v1.w;
+    a2 += v2.x * v2.x + v2.y * v2.y + v2.z * v2.z + v2.w * v2.w;
+    a3 += v3.x * v3.x + v3.y * v3.y + v3.z * v3.z + v3.w * v3.w;
   }
+  for (; i < n4; i += stride) {
+    const float4 v = ld_stream(p + i);
+    a0 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  float acc = (a0 + a1) + (a2 + a3);
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -108,7 +120,26 @@ unit_sumsq_kernel(const float* __restrict__ x, float* __restrict__ sumsq, int64_
 }
 
 // ------------------------------------------------------------------ K13 argmax / K14 masked CE rows
-// one CTA per row (22k floats = 87 KB); first-max tie rule.
+// one CTA per row (22k floats = 87 KB), one pass, 16-byte loads: a row starts at any 4-byte boundary (ld = 22,234), so
+// the first (4 - misalignment) % 4 elements and the tail are read as scalars and the body as float4.
+struct RowSpan {
+  int head;        // scalar elements before the aligned body
+  int n4;          // float4 of the body
+  const float4* body;
+};
+__device__ __forceinline__ RowSpan row_span(const float* row, int N) {
+  RowSpan s;
+  s.head = (int)((4u - ((uint32_t)((uintptr_t)row >> 2) & 3u)) & 3u);
+  if (s.head > N) s.head = N;
+  s.n4 = (N - s.head) >> 2;
+  s.body = reinterpret_cast<const float4*>(row + s.head);
+  return s;
+}
+
+__device__ __forceinline__ void argmax_take(float v, int j, float& best, int& bi) {
+  if (v > best || (v == best && j < bi)) { best = v; bi = j; }          // first-max tie rule of tf.argmax
+}
+
 __global__ void __launch_bounds__(256)
 argmax_rows_kernel(const float* __restrict__ logits, int64_t ld, int32_t* __restrict__ ids, int64_t ids_stride,
                    int M, int N) {
@@ -116,58 +147,76 @@ argmax_rows_kernel(const float* __restrict__ logits, int64_t ld, int32_t* __rest
   __shared__ int si[8];
   const int r = blockIdx.x;
   const float* row = logits + (int64_t)r * ld;
+  const RowSpan sp = row_span(row, N);
   float best = -FLT_MAX;
   int bi = 0x7fffffff;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    float v = __ldg(row + j);
-    if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+  if ((int)threadIdx.x < sp.head) argmax_take(__ldg(row + threadIdx.x), threadIdx.x, best, bi);
+  int j4 = threadIdx.x;
+  for (; j4 + 256 < sp.n4; j4 += 512) {                                    // two independent loads in flight
+    const float4 a = ld_stream(sp.body + j4), b = ld_stream(sp.body + j4 + 256);
+    const int ja = sp.head + 4 * j4, jb = ja + 1024;
+    argmax_take(a.x, ja, best, bi); argmax_take(a.y, ja + 1, best, bi); argmax_take(a.z, ja + 2, best, bi); argmax_take(a.w, ja + 3, best, bi);
+    argmax_take(b.x, jb, best, bi); argmax_take(b.y, jb + 1, best, bi); argmax_take(b.z, jb + 2, best, bi); argmax_take(b.w, jb + 3, best, bi);
   }
+  for (; j4 < sp.n4; j4 += 256) {
+    const float4 a = ld_stream(sp.body + j4);
+    const int ja = sp.head + 4 * j4;
+    argmax_take(a.x, ja, best, bi); argmax_take(a.y, ja + 1, best, bi); argmax_take(a.z, ja + 2, best, bi); argmax_take(a.w, ja + 3, best, bi);
+  }
+  for (int j = sp.head + 4 * sp.n4 + threadIdx.x; j < N; j += 256) argmax_take(__ldg(row + j), j, best, bi);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     float ov = __shfl_xor_sync(0xffffffffu, best, o);
     int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    argmax_take(ov, oi, best, bi);
   }
   if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w)
-      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    for (int w = 1; w < 8; ++w) argmax_take(sv[w], si[w], best, bi);
     ids[(int64_t)r * ids_stride] = bi;
   }
+}
+
+// running (max, sum of exp(v - max)) of a softmax denominator
+__device__ __forceinline__ void lse_take(float v, float& m, float& s) {
+  if (v > m) { s = s * expf(m - v) + 1.0f; m = v; } else { s += expf(v - m); }
+}
+__device__ __forceinline__ void lse_merge(float m2, float s2, float& m, float& s) {
+  const float mm = fmaxf(m, m2);
+  s = s * expf(m - mm) + s2 * expf(m2 - mm);
+  m = mm;
 }
 
 __global__ void __launch_bounds__(256)
 masked_ce_rows_kernel(const float* __restrict__ logits, int64_t ld, const int32_t* __restrict__ target,
                       float* __restrict__ row_loss, int M, int N) {
-  __shared__ float red[8];
-  __shared__ float bcast;
+  __shared__ float red_m[8], red_s[8];
   const int r = blockIdx.x;
   const float* row = logits + (int64_t)r * ld;
-  float mx = -FLT_MAX;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) mx = fmaxf(mx, __ldg(row + j));
-  mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float m = red[0];
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-    bcast = m;
+  const RowSpan sp = row_span(row, N);
+  float m = -FLT_MAX, s = 0.f;                    // exp(-FLT_MAX - v) underflows to 0: an empty lane merges as (., 0)
+  if ((int)threadIdx.x < sp.head) lse_take(__ldg(row + threadIdx.x), m, s);
+  for (int j4 = threadIdx.x; j4 < sp.n4; j4 += 256) {
+    const float4 a = ld_stream(sp.body + j4);
+    // one rescale per float4: max of the four first, then four plain exponentials
+    const float m4 = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
+    if (m4 > m) { s *= expf(m - m4); m = m4; }
+    s += (expf(a.x - m) + expf(a.y - m)) + (expf(a.z - m) + expf(a.w - m));
   }
-  __syncthreads();
-  mx = bcast;
-  float sum = 0.f;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) sum += expf(__ldg(row + j) - mx);
-  sum = warp_sum(sum);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  for (int j = sp.head + 4 * sp.n4 + threadIdx.x; j < N; j += 256) lse_take(__ldg(row + j), m, s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_merge(om, os, m, s);
+  }
+  if ((threadIdx.x & 31) == 0) { red_m[threadIdx.x >> 5] = m; red_s[threadIdx.x >> 5] = s; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w];
+    for (int w = 1; w < 8; ++w) lse_merge(red_m[w], red_s[w], m, s);
     int t = target[r];
     float tv = (t >= 0 && t < N) ? row[t] : 0.f;
-    float ce = (logf(s) + mx) - tv;
+    float ce = (logf(s) + m) - tv;
     row_loss[r] = (t != 0) ? ce : 0.f;
   }
 }
@@ -257,8 +306,9 @@ extern "C" int dsc_unit_sumsq(const float* x, float* sumsq, int n_units, int64_t
   if (n_units == 0) return DSC_OK;
   cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(float) * n_units, as_stream(stream));
   if (e != cudaSuccess) { set_error("dsc_unit_sumsq: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
-  int64_t want = (elems_per_unit / 4 + 255) / 256;
-  int chunks = (int)(want < 32 ? want : 32);
+  // ~8 float4 per thread: a 64-sentence unit (7,936 float4) is 4 CTAs, so 37 units fill the 148 SMs once
+  int64_t want = (elems_per_unit / 4 + 2047) / 2048;
+  int chunks = (int)(want < 1 ? 1 : (want < 64 ? want : 64));
   unit_sumsq_kernel<<<dim3(chunks, n_units), 256, 0, as_stream(stream)>>>(x, sumsq, elems_per_unit);
   return check_launch("dsc_unit_sumsq");
 }
