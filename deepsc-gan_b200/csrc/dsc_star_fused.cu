@@ -176,6 +176,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_cur[4][128];      // relay node of the 4 sentences of the tile
   __shared__ __align__(16) float q_cur[4][128];      // its query under the relay weights
+  __shared__ __align__(16) float bias_s[2][128];     // [satellite dense | relay dense] biases: L1 is thrashed by the key streams
   __shared__ __align__(16) uint32_t patch_w[2][4][4][16];   // [hi|lo][sentence][column quarter]: bf16 pairs of s' for the X patch
   constexpr int parts = (NPASS == 3) ? 2 : 1;
   constexpr uint32_t kArrivals = kCompute;            // one elected arrival per compute warp (after __syncwarp)
@@ -185,6 +186,8 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
   int tr_n = 0;
   for (uint32_t i = tid; i < RB_BYTES / 16; i += sf::kThreads) reinterpret_cast<uint4*>(rb)[i] = make_uint4(0, 0, 0, 0);
   fence_async_smem();
+  if (tid < 128) bias_s[0][tid] = __ldg(bias_o + tid);
+  else if (tid < 256) bias_s[1][tid - 128] = __ldg(bias_r + tid - 128);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_free[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kArrivals); }
@@ -401,20 +404,18 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           tmem_ld32(lane_addr + ACC0 + sub * 32, v);
           tmem_ld_wait();
           free_acc(0);
-          if (lane == 31) {
+          {
+            // warp-uniform code (no divergent relay-lane branch): every lane reads the bias and its sentence's s from
+            // shared memory (broadcast loads), the relay lane keeps s
+            const bool relay_lane = (lane == 31);
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 b4 = reinterpret_cast<const float4*>(&bias_s[0][sub * 32])[q4];
               const float4 s4 = reinterpret_cast<const float4*>(my_s)[q4];
-              v[4*q4] = s4.x; v[4*q4+1] = s4.y; v[4*q4+2] = s4.z; v[4*q4+3] = s4.w;
-            }
-          } else {
-#pragma unroll
-            for (int q4 = 0; q4 < 8; ++q4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_o + sub * 32) + q4);
-              v[4*q4]   = fmaxf(v[4*q4]   + b4.x, 0.f);
-              v[4*q4+1] = fmaxf(v[4*q4+1] + b4.y, 0.f);
-              v[4*q4+2] = fmaxf(v[4*q4+2] + b4.z, 0.f);
-              v[4*q4+3] = fmaxf(v[4*q4+3] + b4.w, 0.f);
+              v[4*q4]   = relay_lane ? s4.x : fmaxf(v[4*q4]   + b4.x, 0.f);
+              v[4*q4+1] = relay_lane ? s4.y : fmaxf(v[4*q4+1] + b4.y, 0.f);
+              v[4*q4+2] = relay_lane ? s4.z : fmaxf(v[4*q4+2] + b4.z, 0.f);
+              v[4*q4+3] = relay_lane ? s4.w : fmaxf(v[4*q4+3] + b4.w, 0.f);
             }
           }
           if (last) {
@@ -422,10 +423,13 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) xr[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
           }
+          DSC_TR(warp ? 512 : 256);
           uint32_t hi[16], lo[16];
           split_quarter_row(v, hi, lo);
+          DSC_TR(warp ? 512 : 256);
           store_quarter_row<NPASS>(lane_addr, AX_HI, AX_LO, sub, hi, lo);   // J0..J3 have completed (their commit precedes J4's)
           tmem_st_wait();
+          DSC_TR(warp ? 512 : 256);
           warp_arrive(&bars.x_ready, 1);
         }
         }   // !(skip0 && c == 0)
@@ -445,6 +449,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           wait_acc(1);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            // (both heads in one 32-column pass with interleaved reductions was tried: more spills, 5 % slower)
             float k[16];
             tmem_ld16(lane_addr + ACC1 + sub * 32 + h * 16, k);
             tmem_ld_wait();
@@ -465,6 +470,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             w1[h] = e1 * inv;
             w2[h] = e2 * inv;
           }
+          DSC_TR(warp ? 512 : 256);
 #pragma unroll
           for (int i = 0; i < 8; ++i) k2[i] = __ldg(kv2 + (32 + i) * 32);      // the values take the keys' registers
           free_acc(1);
@@ -513,7 +519,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           float v = tmem_ld1(lane_addr + ACC0 + sub);
           tmem_ld_wait();
           free_acc(0);
-          v = fmaxf(v + __ldg(bias_r + f), 0.f);
+          v = fmaxf(v + bias_s[1][f], 0.f);
           s_cur[sub][f] = v;
           if (!last) {
             // bf16 hi / lo of s'[sub][f], packed in pairs by the even lanes: operand of J8 (J7 has completed) and the words

@@ -49,14 +49,14 @@ for c in range(cycles):
         n += 1
 names0 = ["x_ready(tile)"]
 per0 = ["J0 acc seen", "J0 acc freed", "J2 acc seen", "J2 acc freed", "ATT staged (t_ready)", "J4 acc seen", "J4 acc freed",
-        "X' staged (x_ready)", "J5 acc seen", "J5 freed", "J6 acc seen", "J6 freed", "att_r staged (t_ready)", "J7 acc seen",
+        "J4 bias+relu done", "J4 hi/lo split done", "J4 tcgen05.st landed", "X' staged (x_ready)", "J5 acc seen", "J5 softmax weights", "J5 freed", "J6 acc seen", "J6 freed", "att_r staged (t_ready)", "J7 acc seen",
         "J7 freed", "s' staged (t_ready)", "s' barrier passed", "relay row patched", "X patched (x_ready)"]
 print("compute warp 0:")
 i = 0
 print(f"  {names0[0]:28s} {us(w0[i]):8.2f}"); i += 1
 for c in range(cycles):
     last = c + 1 == cycles
-    ev = per0[:15] + per0[16:17] if last else per0
+    ev = per0[:19] + per0[20:21] if last else per0
     for name in ev:
         print(f"  c{c} {name:25s} {us(w0[i]):8.2f}")
         i += 1
@@ -67,4 +67,4 @@ for c in range(min(cycles, 2)):
     for name in per8:
         print(f"  c{c} {name:25s} {us(w8[i]):8.2f}")
         i += 1
-    i += (len(per0) if c + 1 < cycles else 16) - len(per8)
+    i += (len(per0) if c + 1 < cycles else 20) - len(per8)
