@@ -54,6 +54,8 @@ _SIGNATURES = {
     "dsc_fgm_normalize": (C.c_int, [vp, vp, f32, i32, i32, i32, vp]),
     # backward kernels (K17)
     "dsc_gemm": (C.c_int, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, i32, i32, vp]),
+    "dsc_gemm_nt_tc": (C.c_int, [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]),
+    "dsc_transpose": (C.c_int, [vp, i64, vp, i64, i32, i32, vp]),
     "dsc_bias_act_backward": (C.c_int, [vp, i64, vp, i64, i32, vp, i64, vp, i32, i32, vp]),
     "dsc_add_layernorm_backward": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, vp]),
     "dsc_mha_attention_backward": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,

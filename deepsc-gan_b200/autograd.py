@@ -16,6 +16,9 @@ from . import _lib
 from ._lib import _check, _ptr, _stream, load
 
 
+TC_GEMM_MIN_MACS = 10 ** 9        # same threshold as gemm_nt_tc_eligible (dsc_gemm_nt_tc.cu)
+
+
 def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
@@ -30,6 +33,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool 
     assert K == K2, (a.shape, b.shape, trans_a, trans_b)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+    if trans_a and not trans_b and M * N * K >= TC_GEMM_MIN_MACS and K % 2 == 0:
+        # dW = X^T @ dY at vocabulary size: both operands are contiguous along the wrong axis for a K-major tensor-core
+        # operand, so they are transposed once ([M,K] and [N,K], K = rows of the batch) and the product runs as A @ B^T
+        at = torch.empty((M, K), device=a.device, dtype=torch.float32)
+        bt = torch.empty((N, K), device=a.device, dtype=torch.float32)
+        _check(load().dsc_transpose(a.data_ptr(), a.stride(0), at.data_ptr(), K, K, M, _stream()), "dsc_transpose")
+        _check(load().dsc_transpose(b.data_ptr(), b.stride(0), bt.data_ptr(), K, K, N, _stream()), "dsc_transpose")
+        _check(load().dsc_gemm_nt_tc(at.data_ptr(), K, bt.data_ptr(), K, out.data_ptr(), out.stride(0), M, N, K,
+                                     int(accumulate), _stream()), "dsc_gemm_nt_tc")
+        return out
     _check(load().dsc_gemm(a.data_ptr(), a.stride(0), int(trans_a), b.data_ptr(), b.stride(0), int(trans_b),
                            out.data_ptr(), out.stride(0), M, N, K, int(accumulate), _stream()), "dsc_gemm")
     return out

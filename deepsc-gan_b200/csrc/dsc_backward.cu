@@ -618,6 +618,12 @@ static int stream_blocks(int64_t n, int per_block = 256) {
 
 using namespace dsc;
 
+namespace dsc {
+bool gemm_nt_tc_eligible(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K);   // dsc_gemm_nt_tc.cu
+int gemm_nt_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N, int K,
+               int accumulate, cudaStream_t s);
+}
+
 extern "C" int dsc_gemm(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b,
                         float* C, int64_t ldc, int M, int N, int K, int accumulate, void* stream) {
   DSC_REQUIRE(A && B && C, "dsc_gemm: null pointer");
@@ -625,6 +631,9 @@ extern "C" int dsc_gemm(const float* A, int64_t lda, int trans_a, const float* B
   DSC_REQUIRE(lda >= (trans_a ? M : K) && ldb >= (trans_b ? K : N), "dsc_gemm: leading dimension too small");
   if (M == 0 || N == 0) return DSC_OK;
   cudaStream_t s = as_stream(stream);
+  // large A * B^T products (both operands contiguous along K) go to the tensor cores in bf16x3
+  if (!trans_a && trans_b && gemm_nt_tc_eligible(A, lda, B, ldb, M, N, K))
+    return gemm_nt_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, s);
   const int tm = (M + 63) / 64, tn = (N + 63) / 64;
   int splits = 1;
   if (K >= 512 && tm * tn < 2 * kSMs) {

@@ -248,6 +248,16 @@ int dsc_fgm_normalize(const float* g, float* p, float epsilon, int n_units, int 
 int dsc_gemm(const float* A, int64_t lda, int trans_a, const float* B, int64_t ldb, int trans_b,
              float* C, int64_t ldc, int M, int N, int K, int accumulate, void* stream);
 
+/* C[M,N] (+)= A[M,K] @ B[N,K]^T on the tensor cores (bf16x3, fp32 accumulate; both operands fp32 row-major, contiguous
+ * along K, 8-byte aligned with even K and leading dimensions; split-K when M*N is small).  dsc_gemm routes its large
+ * trans_a = 0, trans_b = 1 products here (dX = dY @ W^T); the tape calls it directly for dW = X^T @ dY after
+ * dsc_transpose of both operands.  accumulate != 0: C += (atomicAdd). */
+int dsc_gemm_nt_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int M, int N, int K, int accumulate, void* stream);
+
+/* dst[c*ld_dst + r] = src[r*ld_src + c] for r < rows, c < cols (fp32, tiled through shared memory). */
+int dsc_transpose(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols, void* stream);
+
 /* dz = dy * (y > 0) for act = 1 (relu; dz may alias dy), and dbias[c] = sum_r dz[r][c] (dbias NULL: skipped;
  * act = 0: dz is not written, only dbias is produced).  y is the forward output of dsc_linear. */
 int dsc_bias_act_backward(const float* dy, int64_t ld_dy, const float* y, int64_t ld_y, int act,

@@ -67,6 +67,22 @@ def test_gemm_transposes_and_split_k(AG, dev, M, N, K, ta, tb):
     assert rel_err(acc, ref + 1.0) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,ta,tb", [(1920, 128, 22234, 0, 1), (128, 22234, 1920, 1, 0), (300, 200, 20000, 0, 1),
+                                          (130, 9000, 1000, 1, 0)])
+def test_gemm_vocabulary_sized_on_tensor_cores(AG, dev, M, N, K, ta, tb):
+    """The vocabulary-sized backward products (dX = dY @ W^T, dW = X^T @ dY) take the bf16x3 tcgen05 path
+    (dsc_gemm_nt_tc, directly or after dsc_transpose): fp32-class against an fp64 product, with and without accumulate."""
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    ref = (a.t() if ta else a).double() @ (b.t() if tb else b).double()
+    out = AG.gemm(a.to(dev), b.to(dev), bool(ta), bool(tb))
+    assert rel_err(out, ref) < 2e-5
+    acc = torch.ones((M, N), device=dev)
+    AG.gemm(a.to(dev), b.to(dev), bool(ta), bool(tb), out=acc, accumulate=True)
+    assert rel_err(acc, ref + 1.0) < 2e-5
+
+
 def test_linear_layernorm_gradients(AG, dev):
     from deepsc_gan_b200.models.modules import LayerNormalization
     g = torch.Generator().manual_seed(3)
