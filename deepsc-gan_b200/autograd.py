@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import _check, _ptr, _stream, load
 
 
-TC_GEMM_MIN_MACS = 10 ** 9        # same threshold as gemm_nt_tc_eligible (dsc_gemm_nt_tc.cu)
+TC_GEMM_MIN_MACS = 10 ** 9        # the transposing dW route pays two extra launches: vocabulary-sized products only
 
 
 def _c(t: torch.Tensor) -> torch.Tensor:

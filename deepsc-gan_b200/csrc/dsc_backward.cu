@@ -452,39 +452,56 @@ star_pack_backward_kernel(const float* __restrict__ dtile, float* __restrict__ d
 }
 
 // ================================================================== masked CE backward
-// dlogits[r][j] = g[r] * (softmax(logits[r])[j] - [j == t]) for t != 0, else 0.  CTA per row.
+// dlogits[r][j] = g[r] * (softmax(logits[r])[j] - [j == t]) for t != 0, else 0.  CTA per row: ONE read of the row (16-byte
+// loads into shared memory with an online log-sum-exp) and one write, instead of three scalar passes over 87 KB.
 __global__ void __launch_bounds__(256)
 masked_ce_backward_kernel(const float* __restrict__ logits, int64_t ld, const int32_t* __restrict__ target,
                           const float* __restrict__ grow, float* __restrict__ dlogits, int64_t ldd, int N) {
-  __shared__ float red[8];
-  __shared__ float bcast;
+  extern __shared__ float srow[];                 // the row, N floats
+  __shared__ float red_m[8], red_s[8];
   const int r = blockIdx.x;
   const float* row = logits + (int64_t)r * ld;
   float* drow = dlogits + (int64_t)r * ldd;
   const int t = target[r];
   const float g = grow[r];
+  const RowSpan dsp = row_span(drow, N);
+  float4* dbody = reinterpret_cast<float4*>(drow + dsp.head);
   if (t == 0 || g == 0.f) {
-    for (int j = threadIdx.x; j < N; j += blockDim.x) drow[j] = 0.f;
+    if ((int)threadIdx.x < dsp.head) drow[threadIdx.x] = 0.f;
+    for (int j4 = threadIdx.x; j4 < dsp.n4; j4 += 256) dbody[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = dsp.head + 4 * dsp.n4 + threadIdx.x; j < N; j += 256) drow[j] = 0.f;
     return;
   }
-  float mx = -FLT_MAX;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) mx = fmaxf(mx, __ldg(row + j));
-  mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  const RowSpan sp = row_span(row, N);
+  float m = -FLT_MAX, s = 0.f;
+  if ((int)threadIdx.x < sp.head) { const float v = __ldg(row + threadIdx.x); srow[threadIdx.x] = v; lse_take(v, m, s); }
+  for (int j4 = threadIdx.x; j4 < sp.n4; j4 += 256) {
+    const float4 a = ld_stream(sp.body + j4);
+    const int j = sp.head + 4 * j4;
+    srow[j] = a.x; srow[j + 1] = a.y; srow[j + 2] = a.z; srow[j + 3] = a.w;
+    const float m4 = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
+    if (m4 > m) { s *= expf(m - m4); m = m4; }
+    s += (expf(a.x - m) + expf(a.y - m)) + (expf(a.z - m) + expf(a.w - m));
+  }
+  for (int j = sp.head + 4 * sp.n4 + threadIdx.x; j < N; j += 256) { const float v = __ldg(row + j); srow[j] = v; lse_take(v, m, s); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    lse_merge(om, os, m, s);
+  }
+  if ((threadIdx.x & 31) == 0) { red_m[threadIdx.x >> 5] = m; red_s[threadIdx.x >> 5] = s; }
   __syncthreads();
-  if (threadIdx.x == 0) { float m = red[0]; for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]); bcast = m; }
-  __syncthreads();
-  mx = bcast;
-  float sum = 0.f;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) sum += expf(__ldg(row + j) - mx);
-  sum = warp_sum(sum);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; bcast = g / s; }
-  __syncthreads();
-  const float sc = bcast;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) drow[j] = expf(__ldg(row + j) - mx) * sc - (j == t ? g : 0.f);
+  m = red_m[0]; s = red_s[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) lse_merge(red_m[w], red_s[w], m, s);
+  const float sc = g / s;
+  auto out = [&](int j) { return expf(srow[j] - m) * sc - (j == t ? g : 0.f); };
+  if ((int)threadIdx.x < dsp.head) drow[threadIdx.x] = out(threadIdx.x);
+  for (int j4 = threadIdx.x; j4 < dsp.n4; j4 += 256) {
+    const int j = dsp.head + 4 * j4;
+    st_stream(dbody + j4, make_float4(out(j), out(j + 1), out(j + 2), out(j + 3)));
+  }
+  for (int j = dsp.head + 4 * dsp.n4 + threadIdx.x; j < N; j += 256) drow[j] = out(j);
 }
 
 // ================================================================== power norm / channel backward
@@ -767,7 +784,15 @@ extern "C" int dsc_masked_ce_backward(const float* logits, int64_t ld, const int
                                       float* dlogits, int64_t ld_d, int M, int N, void* stream) {
   DSC_REQUIRE(logits && target && grad_rows && dlogits && M >= 0 && N > 0, "dsc_masked_ce_backward: bad argument");
   if (M == 0) return DSC_OK;
-  masked_ce_backward_kernel<<<M, 256, 0, as_stream(stream)>>>(logits, ld, target, grad_rows, dlogits, ld_d, N);
+  const size_t smem = sizeof(float) * (size_t)N;
+  DSC_REQUIRE(smem <= 200 * 1024, "dsc_masked_ce_backward: a row of %d logits does not fit in shared memory", N);
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(masked_ce_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("dsc_masked_ce_backward: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
+    attr_bytes = smem;
+  }
+  masked_ce_backward_kernel<<<M, 256, smem, as_stream(stream)>>>(logits, ld, target, grad_rows, dlogits, ld_d, N);
   return check_launch("dsc_masked_ce_backward");
 }
 

@@ -55,4 +55,33 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
 
 constexpr int kSMs = 148;   // B200
 
+// ---- row helpers of the vocabulary-sized kernels (dsc_rows.cu, dsc_backward.cu)
+// A logits row starts at any 4-byte boundary (ld = 22,234): the first (4 - misalignment) % 4 elements and the tail are
+// read as scalars, the body as float4.
+struct RowSpan {
+  int head;        // scalar elements before the aligned body
+  int n4;          // float4 of the body
+  const float4* body;
+};
+__device__ __forceinline__ RowSpan row_span(const float* row, int N) {
+  RowSpan s;
+  s.head = (int)((4u - ((uint32_t)((uintptr_t)row >> 2) & 3u)) & 3u);
+  if (s.head > N) s.head = N;
+  s.n4 = (N - s.head) >> 2;
+  s.body = reinterpret_cast<const float4*>(row + s.head);
+  return s;
+}
+
+// running (max, sum of exp(v - max)) of a softmax denominator
+__device__ __forceinline__ void lse_take(float v, float& m, float& s) {
+  if (v > m) { s = s * expf(m - v) + 1.0f; m = v; } else { s += expf(v - m); }
+}
+__device__ __forceinline__ void lse_merge(float m2, float s2, float& m, float& s) {
+  const float mm = fmaxf(m, m2);
+  s = s * expf(m - mm) + s2 * expf(m2 - mm);
+  m = mm;
+}
+
+
+
 }  // namespace dsc

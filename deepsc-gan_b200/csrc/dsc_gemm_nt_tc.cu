@@ -193,7 +193,7 @@ zero_matrix_kernel(float* __restrict__ C, int64_t ldc, int rows, int cols) {
 // whether the tensor-core path takes C (+)= A B^T: worth it only when the product is large, and the 8-byte loads of the
 // staging need even leading dimensions and 8-byte aligned bases
 bool gemm_nt_tc_eligible(const float* A, int64_t lda, const float* B, int64_t ldb, int M, int N, int K) {
-  if ((double)M * (double)N * (double)K < 1.0e9) return false;
+  if ((double)M * (double)N * (double)K < 1.6e7) return false;   // from [1984,128] x [128,128]^T up: 16 CTAs of one chunk beat the FFMA kernel
   if ((lda & 1) || (ldb & 1) || (K & 1)) return false;
   return ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 7u) == 0;
 }

@@ -122,20 +122,6 @@ unit_sumsq_kernel(const float* __restrict__ x, float* __restrict__ sumsq, int64_
 // ------------------------------------------------------------------ K13 argmax / K14 masked CE rows
 // one CTA per row (22k floats = 87 KB), one pass, 16-byte loads: a row starts at any 4-byte boundary (ld = 22,234), so
 // the first (4 - misalignment) % 4 elements and the tail are read as scalars and the body as float4.
-struct RowSpan {
-  int head;        // scalar elements before the aligned body
-  int n4;          // float4 of the body
-  const float4* body;
-};
-__device__ __forceinline__ RowSpan row_span(const float* row, int N) {
-  RowSpan s;
-  s.head = (int)((4u - ((uint32_t)((uintptr_t)row >> 2) & 3u)) & 3u);
-  if (s.head > N) s.head = N;
-  s.n4 = (N - s.head) >> 2;
-  s.body = reinterpret_cast<const float4*>(row + s.head);
-  return s;
-}
-
 __device__ __forceinline__ void argmax_take(float v, int j, float& best, int& bi) {
   if (v > best || (v == best && j < bi)) { best = v; bi = j; }          // first-max tie rule of tf.argmax
 }
@@ -176,16 +162,6 @@ argmax_rows_kernel(const float* __restrict__ logits, int64_t ld, int32_t* __rest
     for (int w = 1; w < 8; ++w) argmax_take(sv[w], si[w], best, bi);
     ids[(int64_t)r * ids_stride] = bi;
   }
-}
-
-// running (max, sum of exp(v - max)) of a softmax denominator
-__device__ __forceinline__ void lse_take(float v, float& m, float& s) {
-  if (v > m) { s = s * expf(m - v) + 1.0f; m = v; } else { s += expf(v - m); }
-}
-__device__ __forceinline__ void lse_merge(float m2, float s2, float& m, float& s) {
-  const float mm = fmaxf(m, m2);
-  s = s * expf(m - mm) + s2 * expf(m2 - mm);
-  m = mm;
 }
 
 __global__ void __launch_bounds__(256)
