@@ -244,9 +244,11 @@ def main():
 
     def launch_flops(meta):
         """Algorithmic FLOPs of one dsc_star_cycles_tc launch; a greedy-step launch skips the satellite half of its
-        first cycle (DSC_STAR_FIRST_SAT_DONE: computed once per batch)."""
-        n_sent, cycles, _n2, first_sat_done = meta
+        first cycle (DSC_STAR_FIRST_SAT_DONE: computed once per batch) and the relay half of its last (DSC_STAR_NO_FINAL_RELAY)."""
+        n_sent, cycles, _n2, first_sat_done, no_final_relay = meta
         per_sent = cycles * (SAT_HALF + RELAY_KV + GEMV) + (cycles - 1) * GEMV - (SAT_HALF if first_sat_done else 0)
+        if no_final_relay:                  # the last cycle stops after J4: no relay K|V, no J7, and no J8 for it
+            per_sent -= RELAY_KV + GEMV + (GEMV if cycles > 1 else 0)
         return float(per_sent) * n_sent
 
     passes = {1: 3, 2: 1}.get(args.prec, 0)

@@ -104,6 +104,7 @@ STATS = {"launches": 0}
 # roofline accounting (CUDA events on the launching stream around the single kernel launch)
 PROFILE = None
 STAR_FIRST_SAT_DONE = 0x100          # include/deepsc_b200.h DSC_STAR_FIRST_SAT_DONE
+STAR_NO_FINAL_RELAY = 0x200          # include/deepsc_b200.h DSC_STAR_NO_FINAL_RELAY
 PROFILE_OPS = ("dsc_star_sat_tc", "dsc_star_cycles_tc")
 
 
@@ -330,7 +331,8 @@ def star_cycles_tc(xi0: torch.Tensor, s0: torch.Tensor, q0: torch.Tensor, kvei: 
         assert t.is_contiguous()
     assert kv2i is None or (kv2i.is_contiguous() and kv2i.numel() == n_sent * 8192)
     assert x_rowmajor.numel() == n_sent * 4096 and xi0.numel() >= n_sent * 4096 and kvei.numel() == n_sent * 8192
-    with _timed("dsc_star_cycles_tc", (n_sent, n_cycles, n2, bool(prec & STAR_FIRST_SAT_DONE))):
+    with _timed("dsc_star_cycles_tc", (n_sent, n_cycles, n2, bool(prec & STAR_FIRST_SAT_DONE),
+                                       bool(prec & STAR_NO_FINAL_RELAY))):
         _check(load().dsc_star_cycles_tc(xi0.data_ptr(), s0.data_ptr(), q0.data_ptr(), kvei.data_ptr(), _ptr(kv2i), n2,
                                          packed_weight(w_grouped, 384).data_ptr(), packed_weight(wo, 128).data_ptr(),
                                          packed_weight(wkv_relay, 256).data_ptr(), packed_weight(wo_relay, 128).data_ptr(),

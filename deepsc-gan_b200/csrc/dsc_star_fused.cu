@@ -62,11 +62,23 @@ constexpr uint32_t ACC_Q = ACC1 + 96;                         // J8's 16 columns
 // compute warps are still busy with the satellite attention, instead of delaying J0.
 // skip0: the satellite phase of cycle 0 (J0..J4) was computed by an earlier launch (it depends on the e tile only, not on
 // the decoded prefix): x_tile0 holds X' and cycle 0 is J5, J6, J7.
-__device__ __forceinline__ int jobs_in_cycle(int c, bool skip0) { return c ? JOBS : (skip0 ? 3 : JOBS - 1); }
-__device__ __forceinline__ int job_at(int c, int i, bool skip0) {
-  if (c == 0) return skip0 ? 5 + i : i;
-  return i < 4 ? i : (i == 4 ? 8 : i - 1);
-}
+// nfr ("no final relay"): the caller does not read the relay row of the result (a greedy decoder reads satellite rows only),
+// so the last cycle stops after J4 and needs no relay query either.
+struct Seq {
+  int n_cycles; bool skip0, nfr;
+  __device__ __forceinline__ bool has_relay(int c) const { return !(nfr && c + 1 == n_cycles); }
+  __device__ __forceinline__ bool has_j8(int c) const { return c > 0 && has_relay(c); }
+  __device__ __forceinline__ int jobs(int c) const {
+    const int sat = (c == 0 && skip0) ? 0 : 5;                 // J0..J4
+    return sat + (has_j8(c) ? 1 : 0) + (has_relay(c) ? 3 : 0);  // J8, J5..J7
+  }
+  __device__ __forceinline__ int job_at(int c, int i) const {
+    if (c == 0 && skip0) return 5 + i;
+    if (i < 4) return i;
+    if (has_j8(c)) return i == 4 ? 8 : i - 1;
+    return i;
+  }
+};
 constexpr uint32_t RB_PLANE = 16 * 128;                       // relay-vector operand: one (part, kb) plane = 16 rows x 128 B
 constexpr uint32_t RB_BYTES = 4 * RB_PLANE;                   // 8 KB behind the ring
 
@@ -166,9 +178,10 @@ __global__ void __launch_bounds__(sf::kThreads, 1)
 star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, const float* __restrict__ Q0,
                   const float* __restrict__ KVEI, const float* __restrict__ KV2I, int n2, sf::Weights W,
                   const float* __restrict__ bias_o, const float* __restrict__ bias_r,
-                  float* __restrict__ Xrow, int n_tiles, int n_cycles, int skip0_i) {
+                  float* __restrict__ Xrow, int n_tiles, int n_cycles, int flags) {
   using namespace sf;
-  const bool skip0 = skip0_i != 0;
+  const bool skip0 = (flags & 1) != 0, nfr = (flags & 2) != 0;
+  const Seq seq{n_cycles, skip0, nfr};
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* rb = ring + STAGES * STAGE_BYTES;         // att_r, then s': B operand of the transposed relay GEMVs (rows 4..15 zero)
@@ -209,9 +222,9 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
       uint32_t n = 0;                                   // chunks issued so far
       for (int t = 0; t < my_tiles; ++t)
         for (int c = 0; c < n_cycles; ++c) {
-          const int jobs = jobs_in_cycle(c, skip0);
+          const int jobs = seq.jobs(c);
           for (int ji = 0; ji < jobs; ++ji, ++n) {
-            const int j = job_at(c, ji, skip0);
+            const int j = seq.job_at(c, ji);
             const uint32_t st = n % STAGES;
             mbar_wait(&bars.w_free[st], ((n / STAGES) - 1) & 1);
             const uint8_t* blob; uint32_t rows, row0, n_pad;
@@ -235,9 +248,9 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
       uint32_t n = 0, use0 = 0, use1 = 0, xr = 0, tr = 0;  // chunks consumed, accumulator uses, operand phases consumed
       for (int t = 0; t < my_tiles; ++t)
         for (int c = 0; c < n_cycles; ++c) {
-          const int jobs = jobs_in_cycle(c, skip0);
+          const int jobs = seq.jobs(c);
           for (int ji = 0; ji < jobs; ++ji, ++n) {
-            const int j = job_at(c, ji, skip0);
+            const int j = seq.job_at(c, ji);
             const uint32_t st = n % STAGES, b = (j < 7) ? ((uint32_t)j & 1u) : 0u;                    // J7 -> ACC0
             if (j == 0 || j == 5) { mbar_wait(&bars.x_ready, xr & 1); ++xr; }          // X staged / X' restaged
             if (j == 4 || j == 7 || j == 8) { mbar_wait(&bars.t_ready, tr & 1); ++tr; } // ATT / att_r / s' staged
@@ -323,6 +336,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
         warp_arrive(&bars.x_ready, 1);
       }
       if (!skip0) load_kve(gp);
+      const int j8_per_tile = (n_cycles > 1) ? n_cycles - 1 - (nfr ? 1 : 0) : 0;
 
       for (int c = 0; c < n_cycles; ++c) {
         const bool last = (c + 1 == n_cycles);
@@ -388,9 +402,9 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
         if (gp) use0 += 2; else use1 += 2;                          // the two QKV jobs drained by the other warps
         tmem_st_wait();
         warp_arrive(&bars.t_ready, 1);
-        if (c > 0) {
+        if (seq.has_j8(c)) {
           // J8 (transposed, issued behind J3): q'[sentence sub][feature 32*quarter + lane] = s' @ Wq_relay
-          mbar_wait(&bars.q_full, (uint32_t)(c - 1 + ti * (n_cycles - 1)) & 1u);
+          mbar_wait(&bars.q_full, (uint32_t)(c - 1 + ti * j8_per_tile) & 1u);
           tc_fence_after();
           const float qv = tmem_ld1(lane_addr + ACC_Q + sub);
           tmem_ld_wait();
@@ -424,15 +438,18 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             for (int q4 = 0; q4 < 8; ++q4) xr[q4] = make_float4(v[4*q4], v[4*q4+1], v[4*q4+2], v[4*q4+3]);
           }
           DSC_TR(warp ? 512 : 256);
-          uint32_t hi[16], lo[16];
-          split_quarter_row(v, hi, lo);
-          DSC_TR(warp ? 512 : 256);
-          store_quarter_row<NPASS>(lane_addr, AX_HI, AX_LO, sub, hi, lo);   // J0..J3 have completed (their commit precedes J4's)
-          tmem_st_wait();
-          DSC_TR(warp ? 512 : 256);
-          warp_arrive(&bars.x_ready, 1);
+          if (seq.has_relay(c)) {
+            uint32_t hi[16], lo[16];
+            split_quarter_row(v, hi, lo);
+            DSC_TR(warp ? 512 : 256);
+            store_quarter_row<NPASS>(lane_addr, AX_HI, AX_LO, sub, hi, lo);   // J0..J3 have completed (their commit precedes J4's)
+            tmem_st_wait();
+            DSC_TR(warp ? 512 : 256);
+            warp_arrive(&bars.x_ready, 1);
+          }
         }
         }   // !(skip0 && c == 0)
+        if (!seq.has_relay(c)) break;                                // nfr: the result's relay row is not wanted
 
         // ================= J5 (K -> ACC1), J6 (V -> ACC0): relay attention, heads 2*sub and 2*sub+1, lane = key row
         {
@@ -521,6 +538,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           free_acc(0);
           v = fmaxf(v + bias_s[1][f], 0.f);
           s_cur[sub][f] = v;
+          const bool next_j8 = !last && seq.has_j8(c + 1);
           if (!last) {
             // bf16 hi / lo of s'[sub][f], packed in pairs by the even lanes: operand of J8 (J7 has completed) and the words
             // that warp (quarter = sub, column quarter = quarter) patches into the relay row of X
@@ -531,15 +549,17 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             lw |= __shfl_down_sync(0xffffffffu, lw, 1) << 16;
             if ((lane & 1) == 0) {
               const uint32_t off = ((uint32_t)f >> 6) * RB_PLANE + sw128_offset((uint32_t)sub, (uint32_t)f & 63u);
-              *reinterpret_cast<uint32_t*>(rb + off) = hw;
+              if (next_j8) *reinterpret_cast<uint32_t*>(rb + off) = hw;
               patch_w[0][sub][quarter][lane >> 1] = hw;
               if (NPASS == 3) {
-                *reinterpret_cast<uint32_t*>(rb + 2 * RB_PLANE + off) = lw;
+                if (next_j8) *reinterpret_cast<uint32_t*>(rb + 2 * RB_PLANE + off) = lw;
                 patch_w[1][sub][quarter][lane >> 1] = lw;
               }
             }
-            fence_async_smem();
-            warp_arrive(&bars.t_ready, 1);
+            if (next_j8) {
+              fence_async_smem();
+              warp_arrive(&bars.t_ready, 1);
+            }
           }
           compute_warps_sync();                                              // s' of the four sentences is complete
           DSC_TR(warp ? 512 : 256);
@@ -621,10 +641,10 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
               aligned16(bias_o) && aligned16(bias_o_relay) && aligned16(x_rowmajor), "dsc_star_cycles_tc: misaligned pointer");
   DSC_REQUIRE((((uintptr_t)packed_wqkv_grouped | (uintptr_t)packed_wo | (uintptr_t)packed_wkv_relay | (uintptr_t)packed_wo_relay |
                 (uintptr_t)packed_wq_relay) & 127u) == 0, "dsc_star_cycles_tc: packed weights must be 128-byte aligned");
-  const int skip0 = (prec & DSC_STAR_FIRST_SAT_DONE) ? 1 : 0;
+  const int skip0 = ((prec & DSC_STAR_FIRST_SAT_DONE) ? 1 : 0) | ((prec & DSC_STAR_NO_FINAL_RELAY) ? 2 : 0);   // kernel flags
   prec &= 255;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_cycles_tc: prec must be 1 (bf16x3) or 2 (bf16)");
-  DSC_REQUIRE(!skip0 || n_cycles >= 2, "dsc_star_cycles_tc: DSC_STAR_FIRST_SAT_DONE needs n_cycles >= 2");
+  DSC_REQUIRE(!(skip0 & 1) || n_cycles >= 2, "dsc_star_cycles_tc: DSC_STAR_FIRST_SAT_DONE needs n_cycles >= 2");
   if (n_sent == 0) return DSC_OK;
   if (n2 == 0) kv2 = kv_e;        // rows are read but masked (lane < n2 is false): any readable [n_sent][64][32][4] floats do
   sf::Weights w{reinterpret_cast<const uint8_t*>(packed_wqkv_grouped), reinterpret_cast<const uint8_t*>(packed_wo),

@@ -126,7 +126,7 @@ class StarGreedyDecoder:
                 if li > 0:                                             # memory of layer li = output of layer li-1
                     _lib.star_pack(self.mid, st.tile)
                 x = star_cycles(st.tile, L.multi_att_satellite, st.relay, L.cycle_num, st.kv2, t + 1, st.ws,
-                                kv_e_ready=(li == 0), kv2i=st.kv2i if tc else None)
+                                kv_e_ready=(li == 0), kv2i=st.kv2i if tc else None, relay_row=False)
                 if li + 1 < len(self.layers):
                     _add_ln(x[:, :31], st.tile[:, :31], st.ln_a, st.ln_b, out=self.mid)
                 else:

@@ -320,13 +320,14 @@ def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace, relay:
 
 def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_num: int,
                 kv2: Optional[torch.Tensor] = None, n2: int = 0, ws: Optional[StarWorkspace] = None,
-                kv_e_ready: bool = False, kv2i: Optional[torch.Tensor] = None) -> torch.Tensor:
+                kv_e_ready: bool = False, kv2i: Optional[torch.Tensor] = None, relay_row: bool = True) -> torch.Tensor:
     """The satellite/relay cycle loop of STE/STD/StarTransformer*Layer (models/modules.py:283-306,
     359-378) on star tiles, deduplicated: every node is projected once per cycle, neighbours are
     gathered by index.  e_tile [S,32,128] with row 31 = mean over tokens; returns the tile after
     ``cycle_num`` cycles (rows 0..30 = h, row 31 = s).  kv2 [S, rows, 256] holds k|v of h2 under the
     relay weights (decoder only), of which the first n2 rows are attended; ``kv2i`` is the same cache
-    already in the interleaved layout of the tcgen05 kernels."""
+    already in the interleaved layout of the tcgen05 kernels.  ``relay_row=False``: the caller reads rows 0..30 only
+    (a greedy decoder), so the one-launch kernel skips the relay half of the last cycle (row 31 is then the relay node before its last update)."""
     S = e_tile.shape[0]
     if _DIFF:
         return _star_cycles_diff(e_tile, sat, relay, cycle_num, kv2, n2)
@@ -343,7 +344,8 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
         return _lib.star_cycles_tc(ws.xi1 if skip else ws.xi0, ws.s0, ws.q0, ws.kvei, kv2i, n2, sat._packed("qkv_grouped"),
                                    sat.dense.kernel.detach(), relay._packed("kv"), relay.dense.kernel.detach(),
                                    relay.wq.kernel.detach(), sat.dense.bias.detach(), relay.dense.bias.detach(),
-                                   ws.x, S, cycle_num, PREC | (_lib.STAR_FIRST_SAT_DONE if skip else 0))
+                                   ws.x, S, cycle_num, PREC | (_lib.STAR_FIRST_SAT_DONE if skip else 0)
+                                   | (0 if relay_row else _lib.STAR_NO_FINAL_RELAY))
     if use_tc(S):
         # tcgen05 path: two fused persistent kernels per cycle (projection + satellite attention; dense + relay
         # k|v projection + relay attention) plus the two per-sentence Dense calls of the relay node.

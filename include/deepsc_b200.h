@@ -129,8 +129,11 @@ int dsc_star_mix_tc(const float* att, float* x_tile, float* x_rowmajor, const fl
  * x_rowmajor [n_sent][32][128] receives the tile after n_cycles cycles (rows 0..30 = h, row 31 = s).
  * prec | DSC_STAR_FIRST_SAT_DONE: the satellite half of the FIRST cycle (:287-300) - which depends on the e tile only,
  * not on kv2 - was computed before (rows 0..30 of a 1-cycle call's output, re-interleaved): x_tile0 holds that X' and
- * the first cycle runs its relay half only.  A greedy decoder pays the satellite half once per batch, not per step. */
+ * the first cycle runs its relay half only.  A greedy decoder pays the satellite half once per batch, not per step.
+ * prec | DSC_STAR_NO_FINAL_RELAY: the caller reads the satellite rows only (a greedy decoder: utlis/eval.py:112 takes
+ * predictions[:, -1:]), so the relay half of the LAST cycle is not run: row 31 of x_rowmajor is the relay node before its last update. */
 #define DSC_STAR_FIRST_SAT_DONE 0x100
+#define DSC_STAR_NO_FINAL_RELAY 0x200
 int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, const float* kv_e,
                        const float* kv2, int n2,
                        const void* packed_wqkv_grouped, const void* packed_wo, const void* packed_wkv_relay,

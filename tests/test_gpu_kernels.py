@@ -156,9 +156,19 @@ def test_star_cycles_first_satellite_half_cached(L, dev, S, n2, prec, monkeypatc
     plain = M.star_cycles(tile, sat, relay, 3, kv2, n2, ws, kv_e_ready=True).clone()
     M.prepare_kv_e(tile, sat, ws, relay, first_sat=True)
     assert ws.xi1 is not None
-    cached = M.star_cycles(tile, sat, relay, 3, kv2, n2, ws, kv_e_ready=True)
+    cached = M.star_cycles(tile, sat, relay, 3, kv2, n2, ws, kv_e_ready=True).clone()
     torch.cuda.synchronize()
     assert torch.equal(plain, cached)
+    # DSC_STAR_NO_FINAL_RELAY: satellite rows identical (row 31 then holds the relay node BEFORE the last update)
+    short = M.star_cycles(tile, sat, relay, 3, kv2, n2, ws, kv_e_ready=True, relay_row=False)
+    torch.cuda.synchronize()
+    assert torch.equal(plain[:, :31], short[:, :31])
+    M.prepare_kv_e(tile, sat, ws, relay)                 # and without the cached first half, 1 and 2 cycles
+    for cyc in (1, 2):
+        full = M.star_cycles(tile, sat, relay, cyc, kv2, n2, ws, kv_e_ready=True).clone()
+        part = M.star_cycles(tile, sat, relay, cyc, kv2, n2, ws, kv_e_ready=True, relay_row=False)
+        torch.cuda.synchronize()
+        assert torch.equal(full[:, :31], part[:, :31])
 
 
 @pytest.mark.parametrize("lq,lk,mode", [(31, 31, "pad"), (30, 30, "combined"), (1, 17, "ids"), (30, 31, "pad"), (7, 7, "none")])
