@@ -15,7 +15,6 @@ namespace dsc {
 using namespace tc;
 
 constexpr int TC_BM = 128;
-constexpr int TC_KC = 128;                 // K chunk held in shared memory (2 K-blocks of 64)
 
 // ---------------------------------------------------------------- weight packing
 // blob layout: [part (hi, lo)][K/64 blocks][N_pad rows][128 B swizzled], N_pad = round_up(N, 128).
@@ -38,17 +37,21 @@ pack_weight_kernel(const float* __restrict__ w, int64_t ldw, int K, int N, int n
 }
 
 // ---------------------------------------------------------------- GEMM
-template <int BN, int NPASS>
-__global__ void __launch_bounds__(128, 1)
+// KB = K-blocks of 64 staged per chunk.  KB = 2 (one chunk for K = 128) is the low-latency form for few tiles; KB = 1
+// halves the shared memory (64 KB at BN = 128), so three CTAs share an SM and the load -> convert -> UMMA -> store
+// phases of different tiles overlap: the form for the 73,408-row Dense layers of the channel codec.
+template <int BN, int NPASS, int KB>
+__global__ void __launch_bounds__(128)
 gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ blob, int n_pad,
                const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
                int M, int K, int N, int act, int row_mod, int row_skip) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // A planes: [part][kb(2)][128 rows][128 B]; B planes: [part][kb(2)][BN rows][128 B]
+  // A planes: [part][kb(KB)][128 rows][128 B]; B planes: [part][kb(KB)][BN rows][128 B]
   constexpr uint32_t A_PLANE = TC_BM * 128, B_PLANE = BN * 128;
+  constexpr int KC = KB * 64;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + 4 * A_PLANE;
+  uint8_t* sB = smem + 2 * KB * A_PLANE;
   __shared__ __align__(8) uint64_t bar_b, bar_mma;
   __shared__ uint32_t tmem_base_s;
 
@@ -69,7 +72,7 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
   const uint32_t tmem_d = tmem_base_s;
   constexpr uint32_t IDESC = idesc_bf16_f32(TC_BM, BN);
 
-  const int n_chunks = K / TC_KC;
+  const int n_chunks = K / KC;
   for (int c = 0; c < n_chunks; ++c) {
     if (c > 0) {                       // operands of the previous chunk must be consumed before overwriting
       mbar_wait(&bar_mma, (c - 1) & 1);
@@ -78,27 +81,45 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
     // ---- B: bulk copies of the packed planes for this chunk
     if (tid == 0) {
       constexpr int parts = (NPASS == 3) ? 2 : 1;
-      mbar_expect_tx(&bar_b, parts * 2 * B_PLANE);
+      mbar_expect_tx(&bar_b, parts * KB * B_PLANE);
       for (int p = 0; p < parts; ++p)
-        for (int kb = 0; kb < 2; ++kb)
-          bulk_g2s(sB + (p * 2 + kb) * B_PLANE,
-                   blob + ((size_t)p * kblocks_total + (size_t)(c * 2 + kb)) * g_plane + (size_t)n0 * 128, B_PLANE, &bar_b);
+        for (int kb = 0; kb < KB; ++kb)
+          bulk_g2s(sB + (p * KB + kb) * B_PLANE,
+                   blob + ((size_t)p * kblocks_total + (size_t)(c * KB + kb)) * g_plane + (size_t)n0 * 128, B_PLANE, &bar_b);
     }
-    // ---- A: fp32 rows -> bf16 hi/lo, swizzled K-major.  Warp w handles rows w, w+4, ...; lane l holds k = 4l..4l+3
-    const int kb_l = lane >> 4;                               // which K-block of the chunk this lane writes
-    const uint32_t k_in = (uint32_t)((lane & 15) << 2);       // k offset inside the K-block
+    // ---- A: fp32 rows -> bf16 hi/lo, swizzled K-major.  KB = 2: warp w handles rows w, w+4, ...; lane l holds
+    //      k = 4l..4l+3 of the 128-wide chunk.  KB = 1: half-warps take two rows at a time (16 lanes x 4 k = 64).
+    if (KB == 2) {
+      const int kb_l = lane >> 4;                               // which K-block of the chunk this lane writes
+      const uint32_t k_in = (uint32_t)((lane & 15) << 2);       // k offset inside the K-block
 #pragma unroll 8
-    for (int it = 0; it < 32; ++it) {
-      const int r = warp + 4 * it;
-      const int gr = m0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gr < M) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)gr * ldx + c * TC_KC) + lane);
-      uint32_t h0, l0, h1, l1;
-      split2(v.x, v.y, h0, l0);
-      split2(v.z, v.w, h1, l1);
-      const uint32_t off = kb_l * A_PLANE + sw128_offset((uint32_t)r, k_in);
-      *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
-      if (NPASS == 3) *reinterpret_cast<uint2*>(sA + 2 * A_PLANE + off) = make_uint2(l0, l1);
+      for (int it = 0; it < 32; ++it) {
+        const int r = warp + 4 * it;
+        const int gr = m0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < M) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)gr * ldx + c * KC) + lane);
+        uint32_t h0, l0, h1, l1;
+        split2(v.x, v.y, h0, l0);
+        split2(v.z, v.w, h1, l1);
+        const uint32_t off = kb_l * A_PLANE + sw128_offset((uint32_t)r, k_in);
+        *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
+        if (NPASS == 3) *reinterpret_cast<uint2*>(sA + 2 * A_PLANE + off) = make_uint2(l0, l1);
+      }
+    } else {
+      const uint32_t k_in = (uint32_t)((lane & 15) << 2);
+#pragma unroll 8
+      for (int it = 0; it < 16; ++it) {
+        const int r = 2 * (warp + 4 * it) + (lane >> 4);
+        const int gr = m0 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < M) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)gr * ldx + c * KC) + (lane & 15));
+        uint32_t h0, l0, h1, l1;
+        split2(v.x, v.y, h0, l0);
+        split2(v.z, v.w, h1, l1);
+        const uint32_t off = sw128_offset((uint32_t)r, k_in);
+        *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
+        if (NPASS == 3) *reinterpret_cast<uint2*>(sA + A_PLANE + off) = make_uint2(l0, l1);
+      }
     }
     fence_async_smem();
     __syncthreads();
@@ -114,11 +135,11 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
         const int pa = (pass == 1) ? 1 : 0;                   // pass 0: hi*hi, pass 1: lo*hi, pass 2: hi*lo
         const int pb = (pass == 2) ? 1 : 0;
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
+        for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            uint64_t da = smem_desc_sw128(a_base + (pa * 2 + kb) * A_PLANE + ks * 32);
-            uint64_t db = smem_desc_sw128(b_base + (pb * 2 + kb) * B_PLANE + ks * 32);
+            uint64_t da = smem_desc_sw128(a_base + (pa * KB + kb) * A_PLANE + ks * 32);
+            uint64_t db = smem_desc_sw128(b_base + (pb * KB + kb) * B_PLANE + ks * 32);
             umma_ss(tmem_d, da, db, IDESC, (c > 0 || pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
           }
       }
@@ -270,18 +291,18 @@ static int launch_gemm_tc_ts(const float* x, int64_t ldx, const uint8_t* blob, i
   return check_launch("dsc_linear_tc(ts)");
 }
 
-template <int BN, int NPASS>
+template <int BN, int NPASS, int KB>
 static int launch_gemm_tc(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y,
                           int64_t ldy, int M, int K, int N, int act, int row_mod, int row_skip, cudaStream_t stream) {
-  constexpr size_t smem = 4 * (size_t)TC_BM * 128 + 4 * (size_t)BN * 128 + 1024;
+  constexpr size_t smem = 2 * KB * (size_t)TC_BM * 128 + 2 * KB * (size_t)BN * 128 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, NPASS, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("dsc_linear_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
     attr_set = true;
   }
   dim3 grid(n_pad / BN, (M + TC_BM - 1) / TC_BM);
-  gemm_tc_kernel<BN, NPASS><<<grid, 128, smem, stream>>>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip);
+  gemm_tc_kernel<BN, NPASS, KB><<<grid, 128, smem, stream>>>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip);
   return check_launch("dsc_linear_tc");
 }
 
@@ -332,11 +353,17 @@ extern "C" int dsc_linear_tc(const float* x, int64_t ldx, const void* packed_w, 
     return prec == 1 ? launch_gemm_tc_ts<128, 3>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, ts_swap, s)
                      : launch_gemm_tc_ts<128, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, ts_swap, s);
   }
+  // many row tiles (the channel codec's 73,408-row layers): 64 KB CTAs, three per SM, so that the phases of different
+  // tiles overlap; few tiles (a greedy step's 2,368 rows): one CTA per SM with the whole K = 128 chunk in one pass
+  const bool many = (int64_t)((M + TC_BM - 1) / TC_BM) * (n_pad / 128) >= 2 * kSMs;
+  if (many)
+    return prec == 1 ? launch_gemm_tc<128, 3, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)
+                     : launch_gemm_tc<128, 1, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s);
   const bool wide = (n_pad % 256) == 0;
   if (prec == 1) {
-    return wide ? launch_gemm_tc<256, 3>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)
-                : launch_gemm_tc<128, 3>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s);
+    return wide ? launch_gemm_tc<256, 3, 2>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)
+                : launch_gemm_tc<128, 3, 2>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s);
   }
-  return wide ? launch_gemm_tc<256, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)
-              : launch_gemm_tc<128, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s);
+  return wide ? launch_gemm_tc<256, 1, 2>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)
+              : launch_gemm_tc<128, 1, 2>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s);
 }

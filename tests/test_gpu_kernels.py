@@ -376,7 +376,9 @@ def test_bad_arguments_raise(L, dev):
 
 @pytest.mark.parametrize("prec,tol", [(1, 3e-5), (2, 2e-2)])
 @pytest.mark.parametrize("M,K,N,act", [(128, 128, 128, 0), (1984, 128, 384, 0), (300, 128, 256, 1), (64, 128, 22234, 0),
-                                       (257, 512, 128, 1), (200, 256, 16, 0)])
+                                       (257, 512, 128, 1), (200, 256, 16, 0),
+                                       # >= 296 output tiles: the 64 KB / three-CTAs-per-SM form of the kernel
+                                       (40000, 128, 256, 1), (38001, 512, 128, 0), (40000, 256, 16, 0)])
 def test_linear_tensor_core(L, dev, M, K, N, act, prec, tol):
     """tcgen05 path: bf16x3 split must be fp32-class (<= 3e-5 relative), single bf16 pass ~1e-2."""
     g = torch.Generator().manual_seed(M + K + N)
