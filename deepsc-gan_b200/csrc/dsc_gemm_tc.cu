@@ -54,9 +54,11 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
   uint8_t* sB = smem + 2 * KB * A_PLANE;
   __shared__ __align__(8) uint64_t bar_b, bar_mma;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[BN];                    // the tile's bias columns: per-element global loads stalled the epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  for (int i = tid; i < BN; i += 128) bias_s[i] = (bias != nullptr && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
   const int kblocks_total = K / 64;
   const size_t g_plane = (size_t)n_pad * 128;
 
@@ -107,7 +109,7 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
       }
     } else {
       const uint32_t k_in = (uint32_t)((lane & 15) << 2);
-#pragma unroll 8
+#pragma unroll
       for (int it = 0; it < 16; ++it) {
         const int r = 2 * (warp + 4 * it) + (lane >> 4);
         const int gr = m0 + r;
@@ -167,9 +169,7 @@ gemm_tc_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restri
         float o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          int cc = c0 + q * 4 + e;
-          float t = v[q * 4 + e];
-          if (bias != nullptr && cc < N) t += __ldg(bias + cc);
+          float t = v[q * 4 + e] + bias_s[j * 32 + q * 4 + e];
           if (act == 1) t = fmaxf(t, 0.f);
           o[e] = t;
         }

@@ -55,7 +55,6 @@ constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = 576;
 constexpr int STAGES = 3;
 constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
-constexpr int JOBS = 9;
 constexpr uint32_t ACC_Q = ACC1 + 96;                         // J8's 16 columns: behind the 96 columns of a QKV job
 // Issue order of a cycle: J0..J3, then J8 (the query q' of THIS cycle's relay attention, from the previous cycle's s';
 // absent in cycle 0, whose query is an input), then J4..J7.  J8 sits behind the QKV jobs so that it runs while the
