@@ -85,6 +85,7 @@ struct Bars {
   uint64_t w_full[STAGES], w_free[STAGES];
   uint64_t acc_full[2], acc_free[2];
   uint64_t x_ready, t_ready;
+  uint64_t ta_ready;                        // the first half of ATT (heads 0..3 = K-block 0 of J4's operand) is staged
   uint64_t q_full;                          // the relay query q' (J8) is in its accumulator columns
 };
 struct Weights {
@@ -162,6 +163,24 @@ __device__ __forceinline__ void issue_relay_gemv(uint32_t d_tmem, uint32_t w_bas
                 smem_desc_sw128(v_base + (pv * 2 + kb) * sf::RB_PLANE + ks * 32u), IDESC, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
   }
 }
+// one K-block (64 of the 128 k) of a TS-mode job, all passes: J4 starts on the first half of ATT while the satellite
+// attention of heads 4..7 is still running (K-block-major accumulation order for this job)
+template <int NPASS, int N>
+__device__ __forceinline__ void issue_group_kb(uint32_t tmem_base, uint32_t acc_col, uint32_t a_hi, uint32_t a_lo,
+                                               uint32_t b_base, uint32_t b_plane_bytes, int kb, bool first) {
+  constexpr uint32_t IDESC = idesc_bf16_f32(128, N);
+#pragma unroll
+  for (int pass = 0; pass < NPASS; ++pass) {
+    const uint32_t a_col = (pass == 1) ? a_lo : a_hi;               // hi*hi, lo*hi, hi*lo
+    const uint32_t pb = (pass == 2) ? 1u : 0u;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint64_t db = smem_desc_sw128(b_base + (pb * 2 + kb) * b_plane_bytes + ks * 32u);
+      umma_ts(tmem_base + acc_col, tmem_base + a_col + (uint32_t)(kb * 4 + ks) * 8u, db, IDESC,
+              (first && pass == 0 && ks == 0) ? 0u : 1u);
+    }
+  }
+}
 __device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
 // one fp32 value -> bf16 hi / lo of element (row, k) of the relay-vector operand
 template <int NPASS>
@@ -205,6 +224,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kArrivals); }
     mbar_init(&bars.x_ready, kArrivals);
     mbar_init(&bars.t_ready, kArrivals);
+    mbar_init(&bars.ta_ready, kArrivals);
     mbar_init(&bars.q_full, 1);
     fence_barrier_init();
   }
@@ -244,7 +264,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     {
       const bool leader = elect_one();
       const uint32_t ring_base = smem_u32(ring), rb_base = smem_u32(rb);
-      uint32_t n = 0, use0 = 0, use1 = 0, xr = 0, tr = 0;  // chunks consumed, accumulator uses, operand phases consumed
+      uint32_t n = 0, use0 = 0, use1 = 0, xr = 0, tr = 0, ta = 0;  // chunks consumed, accumulator uses, operand phases consumed
       for (int t = 0; t < my_tiles; ++t)
         for (int c = 0; c < n_cycles; ++c) {
           const int jobs = seq.jobs(c);
@@ -252,7 +272,8 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             const int j = seq.job_at(c, ji);
             const uint32_t st = n % STAGES, b = (j < 7) ? ((uint32_t)j & 1u) : 0u;                    // J7 -> ACC0
             if (j == 0 || j == 5) { mbar_wait(&bars.x_ready, xr & 1); ++xr; }          // X staged / X' restaged
-            if (j == 4 || j == 7 || j == 8) { mbar_wait(&bars.t_ready, tr & 1); ++tr; } // ATT / att_r / s' staged
+            if (j == 7 || j == 8) { mbar_wait(&bars.t_ready, tr & 1); ++tr; }          // att_r / s' staged
+            if (j == 4) { mbar_wait(&bars.ta_ready, ta & 1); ++ta; }                   // first half of ATT staged
             mbar_wait(&bars.w_full[st], (n / STAGES) & 1);
             if (j != 8) {                                                              // J8 has its own columns (ACC_Q); every
               if (b) { mbar_wait(&bars.acc_free[1], (use1 - 1) & 1); ++use1; }         // warp read the previous q' before it
@@ -264,10 +285,17 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             const uint32_t acc = b ? ACC1 : ACC0;
             if (leader) {
               if (j < 4) issue_group<NPASS, 96>(tmem_base, acc, AX_HI, AX_LO, bb, 96u * 128u, 0u);
-              else if (j == 4) issue_group<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0u);
+              else if (j == 4) issue_group_kb<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 0, true);
               else if (j == 7) issue_relay_gemv<NPASS>(tmem_base + acc, bb, rb_base);
               else if (j == 8) issue_relay_gemv<NPASS>(tmem_base + ACC_Q, bb, rb_base);
               else issue_group<NPASS, 128>(tmem_base, acc, AX_HI, AX_LO, bb, 128u * 128u, 0u);
+            }
+            if (j == 4) {                                     // second half of ATT (heads 4..7), then the K-block 1 UMMAs
+              mbar_wait(&bars.t_ready, tr & 1); ++tr;
+              tc_fence_after();
+              if (leader) issue_group_kb<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 1, false);
+            }
+            if (leader) {
               umma_commit(&bars.w_free[st]);
               umma_commit(j == 8 ? &bars.q_full : &bars.acc_full[b]);
             }
@@ -396,7 +424,11 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           // head `head` covers k = 16*head .. 16*head+15 = operand columns 8*head .. 8*head+7
           tmem_st8(lane_addr + AT_HI + head * 8, ohi);
           if (NPASS == 3) tmem_st8(lane_addr + AT_LO + head * 8, olo);
-          if (gi == 0) load_kve(g + 2);                             // e-keys of this warp's second head pair
+          if (gi == 0) {
+            tmem_st_wait();
+            warp_arrive(&bars.ta_ready, 1);                         // heads 0..3 = K-block 0 of J4's operand
+            load_kve(g + 2);                                        // e-keys of this warp's second head pair
+          }
         }
         if (gp) use0 += 2; else use1 += 2;                          // the two QKV jobs drained by the other warps
         tmem_st_wait();
