@@ -48,7 +48,7 @@ for c in range(cycles):
         print(f"  c{c} J{j}: ready {us(iss[2*n]):8.2f}  issued {us(iss[2*n+1]):8.2f}")
         n += 1
 names0 = ["x_ready(tile)"]
-per0 = ["J0 acc seen", "J0 acc freed", "J2 acc seen", "J2 acc freed", "ATT staged (t_ready)", "J4 acc seen", "J4 acc freed",
+per0 = ["J0 acc seen", "J0 acc freed", "ATT heads 0..3 staged (ta_ready)", "J2 acc seen", "J2 acc freed", "ATT staged (t_ready)", "J4 acc seen", "J4 acc freed",
         "J4 bias+relu done", "J4 hi/lo split done", "J4 tcgen05.st landed", "X' staged (x_ready)", "J5 acc seen", "J5 softmax weights", "J5 freed", "J6 acc seen", "J6 freed", "att_r staged (t_ready)", "J7 acc seen",
         "J7 freed", "s' staged (t_ready)", "s' barrier passed", "relay row patched", "X patched (x_ready)"]
 print("compute warp 0:")
@@ -56,15 +56,15 @@ i = 0
 print(f"  {names0[0]:28s} {us(w0[i]):8.2f}"); i += 1
 for c in range(cycles):
     last = c + 1 == cycles
-    ev = per0[:19] + per0[20:21] if last else per0
+    ev = per0[:20] + per0[21:22] if last else per0     # last cycle: no s' staging for a next query, no patch
     for name in ev:
         print(f"  c{c} {name:25s} {us(w0[i]):8.2f}")
         i += 1
-per8 = ["J1 acc seen", "J1 acc freed", "J3 acc seen", "J3 acc freed", "ATT staged (t_ready)"]
+per8 = ["J1 acc seen", "J1 acc freed", "ATT heads 0..3 staged (ta_ready)", "J3 acc seen", "J3 acc freed", "ATT staged (t_ready)"]
 print("compute warp 8 (first events of each cycle are its QKV jobs):")
 i = 1
 for c in range(min(cycles, 2)):
     for name in per8:
         print(f"  c{c} {name:25s} {us(w8[i]):8.2f}")
         i += 1
-    i += (len(per0) if c + 1 < cycles else 20) - len(per8)
+    i += (len(per0) if c + 1 < cycles else 21) - len(per8)
