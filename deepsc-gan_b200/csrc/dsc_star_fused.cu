@@ -24,22 +24,30 @@
 // under J8).
 //
 // Where the time goes (tools/star_trace.py: clock64 stamps of CTA 0 at every hand-off; 2,368 sentences, 8 cycles,
-// 494-508 us, 13.9 us per tile and cycle): J0..J3 until ATT is staged 5.4 us (2.5 us of tensor time; each QKV epilogue
-// holds its accumulator ~0.75 us, longer than its UMMA), J4 + its epilogue 2.3 us, J5/J6 + the relay attention 4.0 us,
-// J7/J8 + the relay-row patch 2.4 us.  Tensor time per tile and cycle is ~5.9 us at 1.965 GHz (24 UMMAs per job at
-// 58 / 74 cycles for N = 96 / 128, ~45 cycles for the N = 16 GEMVs), all of it on the critical path except J6 and J1..J3:
-// the pipe is busy ~36 % of the time (ncu sm__pipe_tensor_cycles_active), the compute warps are issue-bound inside each
-// epilogue burst (smsp__issue_active 33 % on average) and idle while the UMMAs run.
-// Tried in round 1 and dropped, all parity-correct: (a) 8 instead of 16 compute warps: same time in the spilling early
-// version, slower now; (b) two tiles per CTA on the same warps with ATT held in registers: 1.9x slower (spills);
-// (c) two tile pipelines per CTA (8 warps each, ATT in shared memory as an SS-mode operand, single accumulator per
-// tile, shared weight ring, in-order UMMA issue), re-measured after the elected-lane fix: 31 us per PAIR and cycle =
-// exactly two sequential tiles (562 vs 537 us): the tiles fall into lock-step, both epilogues contend for the same four
-// schedulers while the pipe idles, and the per-tile double buffering of J0..J3 is lost; (d) folding the relay-query GEMV
-// into the K|V phase: 6 % slower.  The transposed J7/J8 gave 537 -> ~500 us.
-// Next: a half-cycle phase offset between two resident tiles needs 640 TMEM columns (2 x (X 128 + ACC 128) + ATT 128),
-// so it has to come from splitting each N = 128 job into halves with their own commits (epilogue of half 0 under the
-// UMMA of half 1) and from caching cycle 1's J0..J4, which do not depend on the decoded prefix.
+// 470-480 us, 12.7 us per tile and cycle): J0..J3 until ATT is staged ~5 us (2.5 us of tensor time; the satellite attention
+// of the 8 heads is ~3.9 us of instruction-issue-bound CUDA-core work: 460 instructions per warp and head, of which
+// 166 FFMA and 96 SHFL), J4 + its epilogue ~1.9 us, J5/J6 + the relay attention ~4.0 us, J7 + the relay-row patch ~1.8 us.
+// Tensor time per tile and cycle is ~5.9 us at 1.965 GHz (24 UMMAs per job at 58 / 74 cycles for N = 96 / 128, ~45
+// cycles for the N = 16 GEMVs): the pipe is busy ~37 % of the time (ncu sm__pipe_tensor_cycles_active), the compute
+// warps are issue-bound inside each epilogue burst (smsp__issue_active 36 % on average) and wait while the UMMAs run.
+// What moved the needle in round 1 (537 -> 470 us per launch, and two skipped half-cycles per greedy step): transposed
+// relay GEMVs; QKV accumulators released right after the q|k|v read; the relay query issued behind J3 into spare columns;
+// J4 started on the first K-block of ATT; biases and the relay-lane select from shared memory; suspend-time hints on the
+// mbarrier polls (the polling loops were a quarter of all issued instructions).
+// Tried and dropped, all parity-correct: (a) 8 instead of 16 compute warps: slower; (b) two tiles per CTA on the same
+// warps with ATT held in registers: 1.9x slower (spills); (c) two tile pipelines per CTA (8 warps each, ATT in shared
+// memory, single accumulator per tile, shared weight ring, in-order UMMA issue): 31 us per PAIR and cycle = exactly two
+// sequential tiles - the epilogues of both tiles contend for the same four schedulers, so overlapping them with the
+// other tile's UMMAs buys nothing while the per-tile double buffering is lost; (d) folding the relay-query GEMV into the
+// K|V phase: 6 % slower; (e) 112 registers per thread: not launchable (warps are allocated in fours: 18 warps count as
+// 20, 20 x 32 x 112 > 64 K registers); (f) both relay-attention heads of a warp in one 32-column pass: more spills,
+// 5 % slower; (g) L2 prefetch of the next tile's node states and keys (cp.async.bulk.prefetch.L2): no change or worse;
+// (h) J4's K-block 1 as two column halves with their own commits + J5 issued per K-block: no change (the J4 epilogue
+// is issue-bound, staggering its halves does not shorten it).
+// Next: the bound is the CUDA-core instruction stream of the two attentions between dependent UMMAs.  A second tile in
+// flight only helps with a second set of warps (register file: 96 x 1,152 threads does not fit) or with fewer
+// instructions per epilogue; candidates are the neighbour exchange through shared memory instead of 96 shuffles per
+// warp and head, and a 2-CTA cluster (cta_group::2) that halves the weight stream per SM and frees shared memory.
 //
 // Warps: 0-15 compute (quarter = warp & 3 is the sentence / TMEM lane quarter, sub = warp >> 2 the column quarter),
 // 16 = UMMA issuer, 17 = weight producer.  Every warp owns 32 of the 128 columns of a row.  Arithmetic as in
