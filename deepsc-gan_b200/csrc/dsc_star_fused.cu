@@ -60,7 +60,7 @@ using namespace tc;
 
 namespace sf {
 constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = 576;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
 constexpr uint32_t ACC_Q = ACC1 + 96;                         // J8's 16 columns: behind the 96 columns of a QKV job
