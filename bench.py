@@ -39,7 +39,7 @@ UNIT = "sentences/s"
 SNRS = list(range(19))
 # dram__bytes_read.sum + dram__bytes_write.sum of one star_fused_kernel<3> launch (8 cycles) from the `ncu --set full`
 # capture summarised in profiles/ (keyed by sentences per launch); null when no capture exists for the size that ran
-ROOFLINE_TRAFFIC_BYTES = {2368: 199828480 + 29116672}   # profiles/r01_ncu_star_fused.txt (full 8-cycle launch, n2 = 17)
+ROOFLINE_TRAFFIC_BYTES = {2368: 200217600 + 28533504}   # profiles/r01_ncu_star_fused.txt (full 8-cycle launch, n2 = 17)
 
 
 def load_peaks():
