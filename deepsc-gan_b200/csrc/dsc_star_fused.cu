@@ -24,7 +24,7 @@
 // under J8).
 //
 // Where the time goes (tools/star_trace.py: clock64 stamps of CTA 0 at every hand-off; 2,368 sentences, 8 cycles,
-// 470-480 us, 12.7 us per tile and cycle): J0..J3 until ATT is staged ~5 us (2.5 us of tensor time; the satellite attention
+// ~450 us, 12.1 us per tile and cycle): J0..J3 until ATT is staged ~5 us (2.5 us of tensor time; the satellite attention
 // of the 8 heads is ~3.9 us of instruction-issue-bound CUDA-core work: 460 instructions per warp and head, of which
 // 166 FFMA and 96 SHFL), J4 + its epilogue ~1.9 us, J5/J6 + the relay attention ~4.0 us, J7 + the relay-row patch ~1.8 us.
 // Tensor time per tile and cycle is ~5.9 us at 1.965 GHz (24 UMMAs per job at 58 / 74 cycles for N = 96 / 128, ~45
