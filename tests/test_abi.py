@@ -35,6 +35,27 @@ def test_version_and_error_channel():
     assert rc == -1 and lib.dsc_last_error() == b"detector must in LS and MMSE"
 
 
+def test_new_entry_points_validate_before_touching_the_gpu():
+    """dsc_gemm_nt_tc / dsc_transpose / the star-cycle flags reject bad arguments with DSC_ERR_BAD_ARG (-1) and a message;
+    none of this needs a device."""
+    lib = _lib.load()
+    assert lib.dsc_gemm_nt_tc(None, 128, None, 128, None, 128, 4, 4, 128, 0, None) == -1
+    assert b"null pointer" in lib.dsc_last_error()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.dsc_gemm_nt_tc(p, 127, p, 128, p, 128, 4, 4, 126, 0, None) == -1          # odd leading dimension
+    assert b"8-byte aligned" in lib.dsc_last_error()
+    assert lib.dsc_gemm_nt_tc(p, 128, p, 128, p, 2, 4, 4, 128, 0, None) == -1            # ldc < N
+    assert lib.dsc_transpose(p, 2, p, 8, 8, 8, None) == -1                               # ld_src < cols
+    # DSC_STAR_FIRST_SAT_DONE needs at least two cycles (the cached half is cycle 0's)
+    big = (ctypes.c_float * 4096)()
+    q = ctypes.cast(ctypes.addressof(big) + (-ctypes.addressof(big)) % 128, ctypes.c_void_p)
+    rc = lib.dsc_star_cycles_tc(q, q, q, q, None, 0, q, q, q, q, q, q, q, q, 4, 1, 1 | _lib.STAR_FIRST_SAT_DONE, None)
+    assert rc == -1 and b"n_cycles >= 2" in lib.dsc_last_error()
+    rc = lib.dsc_star_cycles_tc(q, q, q, q, None, 0, q, q, q, q, q, q, q, q, 6, 8, 1, None)
+    assert rc == -1 and b"multiple of 4" in lib.dsc_last_error()
+
+
 def test_product_has_no_cpu_fallback():
     import pytest
     import torch
