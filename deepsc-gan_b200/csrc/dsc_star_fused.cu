@@ -33,7 +33,8 @@
 // What moved the needle in round 1 (537 -> 470 us per launch, and two skipped half-cycles per greedy step): transposed
 // relay GEMVs; QKV accumulators released right after the q|k|v read; the relay query issued behind J3 into spare columns;
 // J4 started on the first K-block of ATT; biases and the relay-lane select from shared memory; suspend-time hints on the
-// mbarrier polls (the polling loops were a quarter of all issued instructions).
+// mbarrier polls (the polling loops were a quarter of all issued instructions); a 2-stage instead of a 3-stage weight
+// ring (470 -> 450 us: the smaller shared-memory carve-out leaves L1 for the key streams and the spill slots).
 // Tried and dropped, all parity-correct: (a) 8 instead of 16 compute warps: slower; (b) two tiles per CTA on the same
 // warps with ATT held in registers: 1.9x slower (spills); (c) two tile pipelines per CTA (8 warps each, ATT in shared
 // memory, single accumulator per tile, shared weight ring, in-order UMMA issue): 31 us per PAIR and cycle = exactly two
@@ -60,7 +61,7 @@ using namespace tc;
 
 namespace sf {
 constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = 576;
-constexpr int STAGES = 2;
+constexpr int STAGES = 2;                                     // 3 stages: 5 % slower (213 KB of shared memory leave too little L1 for the key streams and spill slots)
 constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
 constexpr uint32_t ACC_Q = ACC1 + 96;                         // J8's 16 columns: behind the 96 columns of a QKV job
