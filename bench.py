@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--units", type=int, default=37, help="64-sentence units per step per GPU")
     ap.add_argument("--ref-units", type=int, default=4, help="units per step of the CPU reference arm")
-    ap.add_argument("--cpu-units", type=int, default=8, help="units of the cpu_baseline sample (N=1 only)")
+    ap.add_argument("--cpu-units", type=int, default=32, help="units of the cpu_baseline sample (N=1 only): ~15 s of CPU work")
     ap.add_argument("--prec", type=int, default=1, help="0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -298,7 +298,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         rate, dt = cpu_oracle_rate(args.cpu_units)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{args.cpu_units} units (512 sentences) of the same workload, oracle greedy "
+                                "sample": f"{args.cpu_units} units ({64 * args.cpu_units} sentences) of the same workload, oracle greedy "
                                           f"(last-position logits), {dt:.1f} s wall"}
     print(json.dumps(line))
     if world > 1:
