@@ -6,6 +6,7 @@ returns an error.  There is no CPU or eager fallback.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import os
 from typing import Optional
@@ -31,12 +32,9 @@ _SIGNATURES = {
     "dsc_add_layernorm": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "dsc_star_pack": (C.c_int, [vp, vp, i32, vp]),
     "dsc_star_satellite_attn": (C.c_int, [vp, vp, vp, i32, vp]),
-    "dsc_star_sat_tc": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, vp]),
     "dsc_star_interleave": (C.c_int, [vp, i64, vp, i32, i32, i32, vp]),
     "dsc_star_kv2_put": (C.c_int, [vp, vp, i32, i32, vp]),
-    "dsc_star_mix_tc": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i32, i32, vp]),
     "dsc_target_tail_tc": (C.c_int, [vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i32, vp, i64, vp, i64, i32, i32, vp]),
-    "dsc_star_relay_update": (C.c_int, [vp, vp, vp, vp, vp, vp, i32, vp]),
     "dsc_star_cycles_tc": (C.c_int, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "dsc_star_relay_attn": (C.c_int, [vp, vp, i32, i32, vp, i32, vp]),
     "dsc_mha_attention": (C.c_int, [vp, i64, i64, vp, vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i64, i32, i32,
@@ -69,12 +67,21 @@ _SIGNATURES = {
     "dsc_power_normalize_backward": (C.c_int, [vp, vp, vp, f32, vp, vp, i32, i64, vp]),
     "dsc_channel_backward": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, i32, i64, vp]),
     "dsc_dropout": (C.c_int, [vp, vp, f32, u64, u64, vp, i64, vp]),
-    "dsc_umma_probe": (C.c_int, [i32, i32, i32, vp, vp]),
-    "dsc_debug_star_trace": (C.c_int, [vp]),
     "dsc_adam_step": (C.c_int, [vp, vp, vp, vp, vp, f32, f32, f32, f32, i32, vp, i32, f32, f32, i64, vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def use_debug_library() -> None:
+    """Developer tools only (tools/star_trace.py, tools/umma_probe.py): bind libdeepsc_b200_debug.so - the product sources
+    compiled with -DDSC_DEBUG_TOOLS=1 plus csrc/debug/*.cu (`python deepsc-gan_b200/build.py --debug`) - instead of the
+    product library.  Must be called before the first load()."""
+    global LIB_PATH
+    assert _lib is None, "use_debug_library() must precede the first load()"
+    LIB_PATH = os.path.join(_HERE, "csrc", "libdeepsc_b200_debug.so")
+    _SIGNATURES["dsc_umma_probe"] = (C.c_int, [i32, i32, i32, vp, vp])
+    _SIGNATURES["dsc_debug_star_trace"] = (C.c_int, [vp])
 
 
 def load() -> C.CDLL:
@@ -105,7 +112,7 @@ STATS = {"launches": 0}
 PROFILE = None
 STAR_FIRST_SAT_DONE = 0x100          # include/deepsc_b200.h DSC_STAR_FIRST_SAT_DONE
 STAR_NO_FINAL_RELAY = 0x200          # include/deepsc_b200.h DSC_STAR_NO_FINAL_RELAY
-PROFILE_OPS = ("dsc_star_sat_tc", "dsc_star_cycles_tc")
+PROFILE_OPS = ("dsc_star_cycles_tc",)
 
 
 class _timed:
@@ -174,7 +181,8 @@ def embed(ids: torch.Tensor, table: torch.Tensor, pos_table: torch.Tensor, pos0:
     return out
 
 
-_PACK_CACHE = {}
+_PACK_CACHE = collections.OrderedDict()      # key -> [stamp, blob, source weight, pinned]
+_PACK_CACHE_MAX = 512
 # bumped by anything that rewrites parameters through raw pointers (the Adam kernel): torch's own _version counter
 # does not see those writes, and the packed / padded weight caches key on both
 WEIGHT_EPOCH = 0
@@ -192,30 +200,37 @@ def weights_changed() -> None:
 
 
 def packed_weight(w: torch.Tensor, n: int) -> torch.Tensor:
-    """bf16 hi/lo UMMA image of a Keras-layout weight, cached per storage and re-packed in place when the weight
-    has been modified (torch version counter or WEIGHT_EPOCH)."""
+    """bf16 hi/lo UMMA image of a Keras-layout weight, cached per storage and re-packed IN PLACE when the weight has
+    been modified (torch version counter or WEIGHT_EPOCH), so the blob address is stable for the life of the entry.
+    An entry touched while a CUDA graph is being captured is pinned: the graph has the blob's raw pointer baked in
+    (and re-packs into it on replay), so it is never evicted.  Other entries are evicted least-recently-used beyond
+    _PACK_CACHE_MAX; eviction only drops the cache's reference, a caller still holding the blob keeps it alive."""
     key = (w.data_ptr(), tuple(w.shape), w.stride(0), n, w.device.index)
     stamp = (w._version, WEIGHT_EPOCH)
     hit = _PACK_CACHE.get(key)
-    if hit is None or hit[0] != stamp:
-        K = w.shape[0]
-        if hit is None:
-            if len(_PACK_CACHE) > 512:
-                _PACK_CACHE.clear()
-            blob = torch.empty((load().dsc_packed_weight_bytes(K, n),), device=w.device, dtype=torch.uint8)
-        else:
-            blob = hit[1]
-        _check(load().dsc_pack_weight(_f32(w).data_ptr(), w.stride(0), K, n, blob.data_ptr(), _stream()),
-               "dsc_pack_weight")
-        hit = (stamp, blob, w)   # keep the source alive so its data_ptr cannot be recycled under the key
+    capturing = torch.cuda.is_current_stream_capturing()
+    if hit is None:
+        blob = torch.empty((load().dsc_packed_weight_bytes(w.shape[0], n),), device=w.device, dtype=torch.uint8)
+        hit = [None, blob, w, capturing]     # the source is kept alive so its data_ptr cannot be recycled under the key
         _PACK_CACHE[key] = hit
+        if len(_PACK_CACHE) > _PACK_CACHE_MAX:
+            for k in [k for k, e in _PACK_CACHE.items() if not e[3] and k != key][: len(_PACK_CACHE) - _PACK_CACHE_MAX * 3 // 4]:
+                del _PACK_CACHE[k]
+    else:
+        _PACK_CACHE.move_to_end(key)
+        hit[3] = hit[3] or capturing
+    if hit[0] != stamp:
+        _check(load().dsc_pack_weight(_f32(w).data_ptr(), w.stride(0), w.shape[0], n, hit[1].data_ptr(), _stream()),
+               "dsc_pack_weight")
+        hit[0] = stamp
     return hit[1]
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], act: int = 0,
            out: Optional[torch.Tensor] = None, n: Optional[int] = None, row_mod: int = 0, row_skip: int = 0,
-           prec: int = 0) -> torch.Tensor:
-    """y = act(x @ w + bias).  x [M, K] (row stride free), w [K, >=N] Keras layout, out [M, N] (row stride free)."""
+           prec: int = 1) -> torch.Tensor:
+    """y = act(x @ w + bias).  x [M, K] (row stride free), w [K, >=N] Keras layout, out [M, N] (row stride free).
+    prec 1 / 2: tcgen05 (bf16x3 / bf16) when K is a multiple of 128; prec 0, or any other K: the fp32 FFMA kernel."""
     _need_cuda(x, w, bias, out)
     assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.stride(1) == 1
     M, K = x.shape
@@ -293,34 +308,6 @@ def star_kv2_put(vals: torch.Tensor, kv2i: torch.Tensor, row_index: int) -> None
            "dsc_star_kv2_put")
 
 
-def star_sat_tc(xi: torch.Tensor, s_relay: torch.Tensor, kvei: torch.Tensor, w_grouped: torch.Tensor, atti: torch.Tensor,
-                n_sent: int, prec: int) -> torch.Tensor:
-    """Fused projection + satellite attention on interleaved tiles; w_grouped = head-pair-grouped [128,384] weight."""
-    _need_cuda(xi, s_relay, kvei, w_grouped, atti)
-    assert xi.is_contiguous() and kvei.is_contiguous() and atti.is_contiguous() and s_relay.is_contiguous()
-    blob = packed_weight(w_grouped, 384)
-    with _timed("dsc_star_sat_tc", n_sent):
-        _check(load().dsc_star_sat_tc(xi.data_ptr(), s_relay.data_ptr(), kvei.data_ptr(), blob.data_ptr(),
-                                      atti.data_ptr(), n_sent, prec, _stream()), "dsc_star_sat_tc")
-    return atti
-
-
-def star_mix_tc(atti: torch.Tensor, xi: torch.Tensor, x_rowmajor: Optional[torch.Tensor], s_relay: torch.Tensor,
-                wo: torch.Tensor, bias_o: torch.Tensor, wkv_relay: torch.Tensor, q_relay: torch.Tensor,
-                kv2i: Optional[torch.Tensor], n2: int, att_relay: torch.Tensor, n_sent: int, prec: int) -> torch.Tensor:
-    """Fused Wo dense + relu + relay k|v projection + relay attention (see include/deepsc_b200.h)."""
-    _need_cuda(atti, xi, x_rowmajor, s_relay, wo, bias_o, wkv_relay, q_relay, kv2i, att_relay)
-    for t in (atti, xi, s_relay, q_relay, att_relay):
-        assert t.is_contiguous()
-    assert x_rowmajor is None or x_rowmajor.is_contiguous()
-    assert kv2i is None or (kv2i.is_contiguous() and kv2i.numel() == n_sent * 8192)
-    _check(load().dsc_star_mix_tc(atti.data_ptr(), xi.data_ptr(), _ptr(x_rowmajor), s_relay.data_ptr(),
-                                  packed_weight(wo, 128).data_ptr(), packed_weight(wkv_relay, 256).data_ptr(),
-                                  bias_o.data_ptr(), q_relay.data_ptr(), _ptr(kv2i), n2, att_relay.data_ptr(), n_sent,
-                                  prec, _stream()), "dsc_star_mix_tc")
-    return att_relay
-
-
 def star_cycles_tc(xi0: torch.Tensor, s0: torch.Tensor, q0: torch.Tensor, kvei: torch.Tensor, kv2i: Optional[torch.Tensor],
                    n2: int, w_grouped: torch.Tensor, wo: torch.Tensor, wkv_relay: torch.Tensor, wo_relay: torch.Tensor,
                    wq_relay: torch.Tensor, bias_o: torch.Tensor, bias_o_relay: torch.Tensor, x_rowmajor: torch.Tensor,
@@ -358,16 +345,6 @@ def target_tail_tc(attn: torch.Tensor, resid: torch.Tensor, wo: torch.Tensor, bi
                                      _ptr(kv_rows), 0 if kv_rows is None else kv_rows.stride(0),
                                      _ptr(h2_out), 0 if h2_out is None else h2_out.stride(0), M, prec, _stream()),
            "dsc_target_tail_tc")
-
-
-def star_relay_update(att_r: torch.Tensor, wo: torch.Tensor, bo: torch.Tensor, wq: torch.Tensor, s_out: torch.Tensor,
-                      q_out: torch.Tensor) -> None:
-    """s_out = relu(att_r @ wo + bo); q_out = s_out @ wq (fp32)."""
-    _need_cuda(att_r, wo, bo, wq, s_out, q_out)
-    for t in (att_r, wo, wq, s_out, q_out):
-        assert t.is_contiguous()
-    _check(load().dsc_star_relay_update(att_r.data_ptr(), wo.data_ptr(), bo.data_ptr(), wq.data_ptr(), s_out.data_ptr(),
-                                        q_out.data_ptr(), att_r.shape[0], _stream()), "dsc_star_relay_update")
 
 
 def star_relay_attn(qkv_r: torch.Tensor, kv2: Optional[torch.Tensor], n2: int, out: torch.Tensor, n_sent: int):
@@ -466,7 +443,7 @@ def _vocab_tc_workspace(M: int, n_vocab: int, device) -> torch.Tensor:
 
 def vocab_argmax(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n_vocab: int, ids_out: torch.Tensor,
                  logits: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None,
-                 prec: int = 0) -> torch.Tensor:
+                 prec: int = 1) -> torch.Tensor:
     """ids_out [M] int32 view (any stride) <- argmax(x @ w[:, :n_vocab] + bias)."""
     _need_cuda(x, w, bias, ids_out, logits, workspace)
     M = x.shape[0]

@@ -314,92 +314,3 @@ extern "C" int dsc_fgm_normalize(const float* g, float* p, float epsilon, int n_
       g, p, epsilon, samples_per_unit, elems_per_sample);
   return check_launch("dsc_fgm_normalize");
 }
-
-// ------------------------------------------------------------------ relay node update (per sentence GEMVs)
-// s' = relu(att_r @ Wo + bo);  q' = s' @ Wq   (models/modules.py:305-306 dense + relu, and the next cycle's wq).
-// fp32 FFMA.  One CTA of 256 threads per 16 sentences.  Warp w owns output columns 16w..16w+15; lane = (kq, c4):
-// kq = lane/4 selects a 16-wide slice of K, c4 = lane%4 a float4 of columns.  Each thread issues its 16 weight
-// loads up front (one memory latency), accumulates 16 sentences x 4 columns, and the 8 K-slices are summed
-// with warp shuffles.
-namespace dsc {
-constexpr int RU_G = 16;
-__device__ __forceinline__ void relay_gemv(const float (*in_s)[128], const float* __restrict__ w, float (&acc)[RU_G][4],
-                                           int kq, int col0) {
-  float4 wv[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(w + (kq * 16 + i) * 128 + col0));
-#pragma unroll
-  for (int g = 0; g < RU_G; ++g) { acc[g][0] = acc[g][1] = acc[g][2] = acc[g][3] = 0.f; }
-#pragma unroll
-  for (int i4 = 0; i4 < 4; ++i4) {
-#pragma unroll
-    for (int g = 0; g < RU_G; ++g) {
-      const float4 a = *reinterpret_cast<const float4*>(&in_s[g][kq * 16 + i4 * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 ww = wv[i4 * 4 + j];
-        acc[g][0] = fmaf(av[j], ww.x, acc[g][0]);
-        acc[g][1] = fmaf(av[j], ww.y, acc[g][1]);
-        acc[g][2] = fmaf(av[j], ww.z, acc[g][2]);
-        acc[g][3] = fmaf(av[j], ww.w, acc[g][3]);
-      }
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < RU_G; ++g)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v = acc[g][c];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      acc[g][c] = v;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-relay_update_kernel(const float* __restrict__ att_r, const float* __restrict__ wo, const float* __restrict__ bo,
-                    const float* __restrict__ wq, float* __restrict__ s_out, float* __restrict__ q_out, int n_sent) {
-  __shared__ __align__(16) float in_s[RU_G][128];
-  __shared__ __align__(16) float mid_s[RU_G][128];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kq = lane >> 2, col0 = warp * 16 + (lane & 3) * 4;
-  const int s0 = blockIdx.x * RU_G;
-  for (int idx = threadIdx.x; idx < RU_G * 32; idx += 256) {
-    const int g = idx >> 5, c4 = idx & 31;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (s0 + g < n_sent) v = __ldg(reinterpret_cast<const float4*>(att_r + (int64_t)(s0 + g) * 128) + c4);
-    *reinterpret_cast<float4*>(&in_s[g][c4 * 4]) = v;
-  }
-  __syncthreads();
-  float acc[RU_G][4];
-  relay_gemv(in_s, wo, acc, kq, col0);
-  if (kq == 0) {
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bo + col0));
-#pragma unroll
-    for (int g = 0; g < RU_G; ++g) {
-      const float4 o = make_float4(fmaxf(acc[g][0] + b4.x, 0.f), fmaxf(acc[g][1] + b4.y, 0.f),
-                                   fmaxf(acc[g][2] + b4.z, 0.f), fmaxf(acc[g][3] + b4.w, 0.f));
-      *reinterpret_cast<float4*>(&mid_s[g][col0]) = o;
-      if (s0 + g < n_sent) *reinterpret_cast<float4*>(s_out + (int64_t)(s0 + g) * 128 + col0) = o;
-    }
-  }
-  __syncthreads();
-  relay_gemv(mid_s, wq, acc, kq, col0);
-  if (kq == 0) {
-#pragma unroll
-    for (int g = 0; g < RU_G; ++g)
-      if (s0 + g < n_sent)
-        *reinterpret_cast<float4*>(q_out + (int64_t)(s0 + g) * 128 + col0) = make_float4(acc[g][0], acc[g][1], acc[g][2], acc[g][3]);
-  }
-}
-}  // namespace dsc
-
-extern "C" int dsc_star_relay_update(const float* att_relay, const float* wo, const float* bo, const float* wq,
-                                     float* s_out, float* q_out, int n_sent, void* stream) {
-  DSC_REQUIRE(att_relay && wo && bo && wq && s_out && q_out && n_sent >= 0, "dsc_star_relay_update: bad argument");
-  if (n_sent == 0) return DSC_OK;
-  dsc::relay_update_kernel<<<(n_sent + dsc::RU_G - 1) / dsc::RU_G, 256, 0, as_stream(stream)>>>(att_relay, wo, bo, wq, s_out, q_out, n_sent);
-  return check_launch("dsc_star_relay_update");
-}

@@ -152,7 +152,11 @@ __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
 // Debug timeline (tools/star_trace.py): when a buffer is registered with dsc_debug_star_trace, CTA 0 stamps clock64()
 // at the hand-offs of its first tile: issuer [0, 256) = (operands ready, UMMAs + commits issued) per job; compute warp 0
 // [256, 512) and warp 8 [512, 768) = their accumulator-seen / operand-staged events in program order.
+#ifdef DSC_DEBUG_TOOLS
 __device__ unsigned long long* g_star_trace = nullptr;
+#else
+#define g_star_trace ((unsigned long long*)nullptr)
+#endif
 #define DSC_TR(base) do { if (TRACE) { if (tr_buf && tr_n < 256) tr_buf[(base) + tr_n] = (unsigned long long)clock64(); ++tr_n; } } while (0)
 
 // relay GEMVs (J7, J8) in transposed form: D[feature][sentence] = W^T (A, the streamed chunk, M = 128) x vectors (B, N = 16
@@ -645,7 +649,10 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
 
 using namespace dsc;
 
+#ifdef DSC_DEBUG_TOOLS
+#include "debug/deepsc_b200_debug.h"
 static bool g_star_trace_on = false;
+#endif
 
 template <int NPASS, bool TRACE>
 static int launch_star_fused(const float* xi0, const float* s0, const float* q0, const float* kvei, const float* kv2i, int n2,
@@ -659,6 +666,7 @@ static int launch_star_fused(const float* xi0, const float* s0, const float* q0,
   return check_launch("dsc_star_cycles_tc");
 }
 
+#ifdef DSC_DEBUG_TOOLS
 extern "C" int dsc_debug_star_trace(void* device_buffer_768_u64) {
   unsigned long long* p = reinterpret_cast<unsigned long long*>(device_buffer_768_u64);
   cudaError_t e = cudaMemcpyToSymbol(dsc::g_star_trace, &p, sizeof(p));
@@ -666,6 +674,7 @@ extern "C" int dsc_debug_star_trace(void* device_buffer_768_u64) {
   g_star_trace_on = p != nullptr;
   return DSC_OK;
 }
+#endif
 
 extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, const float* kv_e,
                                   const float* kv2, int n2,
@@ -692,9 +701,11 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
                 reinterpret_cast<const uint8_t*>(packed_wq_relay)};
   cudaStream_t st = as_stream(stream);
   const int n_tiles = n_sent / 4;
+#ifdef DSC_DEBUG_TOOLS
   if (g_star_trace_on)
     return prec == 1 ? launch_star_fused<3, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st)
                      : launch_star_fused<1, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st);
+#endif
   return prec == 1 ? launch_star_fused<3, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st)
                    : launch_star_fused<1, false>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st);
 }

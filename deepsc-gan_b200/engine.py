@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .models import modules as M
-from .models.modules import StarWorkspace, prepare_kv_e, star_cycles, use_tc, _add_ln
+from .models.modules import StarWorkspace, prepare_kv_e, star_cycles, use_tc, _add_ln, _pad4
 
 START_IDX = 1
 
@@ -80,6 +80,9 @@ class StarGreedyDecoder:
     def __init__(self, net, n_sent: int, max_length: int = 30):
         dec = net.semantic_decoder
         dev = dec.embedding.embeddings.device
+        self.n_real = n_sent
+        if use_tc():
+            n_sent = (n_sent + 3) // 4 * 4             # whole tiles; a ragged batch is zero-padded and trimmed again
         self.net, self.dec, self.n, self.max_length, self.dev = net, dec, n_sent, max_length, dev
         if isinstance(dec, M.SD):
             L = dec.dec_layers
@@ -96,11 +99,14 @@ class StarGreedyDecoder:
 
     def decode(self, received: torch.Tensor, start_idx: int = START_IDX) -> torch.Tensor:
         net, dec, S = self.net, self.dec, self.n
+        if received.shape[0] != S:
+            assert received.shape[0] == self.n_real
+            received = _pad4(received)
         mem = net.channel_decoder.call(received)                      # hoisted out of the step loop
         st0 = self.layers[0]
         _lib.star_pack(mem.contiguous(), st0.tile)
         prepare_kv_e(st0.tile, st0.layer.multi_att_satellite, st0.ws, st0.relay, first_sat=True)
-        tc = use_tc(S)
+        tc = use_tc()
         self.outputs.zero_()
         self.outputs[:, 0] = start_idx
         wf, bf = dec.final_layer.padded_kernel(), dec.final_layer.bias.detach()
@@ -133,7 +139,7 @@ class StarGreedyDecoder:
                     _add_ln(x[:, 30:31], st.tile[:, 30:31], st.ln_a, st.ln_b, out=self.last)
             _lib.vocab_argmax(self.last.view(S, 128), wf, bf, self.vocab, self.outputs[:, t + 1],
                               workspace=self.logit_ws, prec=M.PREC)
-        return self.outputs
+        return self.outputs[: self.n_real]
 
 
 class BaselineGreedyDecoder:
@@ -208,7 +214,7 @@ class GraphedDecoder:
             self._inp.copy_(inp)
         self.graph.replay()
         _lib.STATS["launches"] += self.launches
-        return self.dec.outputs
+        return self.dec.outputs[: getattr(self.dec, "n_real", self.dec.outputs.shape[0])]
 
 
 def make_decoder(net, n_sent: int, max_length: int = 30, graph: Optional[bool] = None):

@@ -21,7 +21,6 @@ SURVEY.md K17), out of place, so that ``utlis`` can take d(loss)/d(symbols) and 
 from __future__ import annotations
 
 import math
-import os
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -32,14 +31,16 @@ from .. import _lib
 from .. import autograd as AG
 
 D_MODEL = 128
-PREC = 0   # precision knob passed to dsc_linear: 0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16
-# tcgen05 star cycles: True = all cycles of a layer in one persistent launch (dsc_star_cycles_tc),
-# False = two fused launches per cycle (dsc_star_sat_tc + dsc_star_mix_tc) plus the relay update
-STAR_FUSED = os.environ.get("DSC_STAR_FUSED", "1") != "0"
+# Arithmetic of every Dense / star-cycle kernel (the `prec` argument of include/deepsc_b200.h):
+#   1 (default)  tcgen05 bf16x3: three bf16 UMMA passes per fp32-class product, fp32 accumulation in TMEM
+#   2            tcgen05 bf16, one pass (throughput experiments; not parity-grade)
+#   0            fp32 FFMA kernels - a debugging aid to separate arithmetic from logic errors, selected explicitly with
+#                set_precision(0); it is also what the backward tape uses for the products with K < 128
+PREC = 1
 
 
 def set_precision(prec: int) -> None:
-    """Select the Dense kernel family used by every module (see include/deepsc_b200.h dsc_linear)."""
+    """Select the arithmetic of every module (see PREC above and include/deepsc_b200.h dsc_linear)."""
     global PREC
     assert prec in (0, 1, 2)
     PREC = prec
@@ -271,7 +272,6 @@ class StarWorkspace:
         self.att = torch.empty((n_sent * 32, 128), **f)
         self.att_r = torch.empty((n_sent, 128), **f)
         self.q_r = torch.empty((n_sent, 128), **f)
-        self.s_buf = torch.empty((n_sent, 128), **f)        # relay nodes (tcgen05 path)
         self.kvei = None                                    # interleaved k|v of the e rows (tcgen05 path)
         self.kv2i = None                                    # interleaved h2 cache built from a row-major kv2
         self.xi0 = None                                     # interleaved e tile, s0 and q0 = s0 @ wq_relay: the
@@ -285,8 +285,20 @@ class StarWorkspace:
         return self.kvei
 
 
-def use_tc(n_sent: int) -> bool:
-    return PREC != 0 and n_sent % 4 == 0
+def use_tc(n_sent: int = 4) -> bool:
+    """True when the star cycles run on the fused tcgen05 kernel (every precision mode but the fp32 debug mode)."""
+    return PREC != 0
+
+
+def _pad4(t: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the sentence axis to a multiple of 4 (one tile of the tcgen05 star kernel = 4 sentences).  A ragged last
+    batch (dataset/dataloader.py:14 batches without drop_remainder) takes this path; whole 64-sentence units never do."""
+    S = t.shape[0]
+    if S % 4 == 0:
+        return t
+    out = torch.zeros((S + 3) // 4 * 4, *t.shape[1:], device=t.device, dtype=t.dtype)
+    out[:S] = t
+    return out
 
 
 def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace, relay: Optional[sublayer1] = None,
@@ -294,28 +306,28 @@ def prepare_kv_e(e_tile: torch.Tensor, sat: sublayer1, ws: StarWorkspace, relay:
     """Everything that depends on the e tile only (constant over cycles and greedy steps): k|v of the e rows under the
     satellite weights and, for the one-launch tcgen05 kernel, the interleaved e tile, s0 and q0 = s0 @ wq_relay.
     ``first_sat``: also the satellite half of the FIRST cycle (models/modules.py:287-300 reads h = e, s = mean(e) and
-    the e keys only), so that a greedy decoder runs it once per batch instead of once per step."""
+    the e keys only), so that a greedy decoder runs it once per batch instead of once per step.
+    e_tile [S,32,128] with S = ws.n (a multiple of 4 in the tcgen05 modes)."""
     S = e_tile.shape[0]
     _lib.linear(e_tile.view(S * 32, 128), sat._packed("kv"), None, out=ws.kv_e, prec=PREC)
-    if use_tc(S):
+    if use_tc() and relay is not None:
         _lib.star_interleave(ws.kv_e.view(S // 4, 128, 256), ws.tc_buffers(), 128)
-        if STAR_FUSED and relay is not None:
-            f = dict(device=e_tile.device, dtype=torch.float32)
-            if ws.xi0 is None:
-                ws.xi0, ws.s0, ws.q0 = torch.empty((S * 4096,), **f), torch.empty((S, 128), **f), torch.empty((S, 128), **f)
-            _lib.star_interleave(e_tile.view(S // 4, 128, 128), ws.xi0, 128)
-            ws.s0.copy_(e_tile[:, 31, :])
-            _lib.linear(ws.s0, relay.wq.kernel.detach(), None, out=ws.q0, prec=PREC)
-            ws.xi1 = None
-            if first_sat:
-                # one cycle without target keys: rows 0..30 of the result are X' = relu(ATT @ Wo + b) of cycle 0
-                _lib.star_cycles_tc(ws.xi0, ws.s0, ws.q0, ws.kvei, None, 0, sat._packed("qkv_grouped"),
-                                    sat.dense.kernel.detach(), relay._packed("kv"), relay.dense.kernel.detach(),
-                                    relay.wq.kernel.detach(), sat.dense.bias.detach(), relay.dense.bias.detach(),
-                                    ws.x, S, 1, PREC)
-                if ws.xi1_buf is None:
-                    ws.xi1_buf = torch.empty((S * 4096,), **f)
-                ws.xi1 = _lib.star_interleave(ws.x.view(S // 4, 128, 128), ws.xi1_buf, 128)
+        f = dict(device=e_tile.device, dtype=torch.float32)
+        if ws.xi0 is None:
+            ws.xi0, ws.s0, ws.q0 = torch.empty((S * 4096,), **f), torch.empty((S, 128), **f), torch.empty((S, 128), **f)
+        _lib.star_interleave(e_tile.view(S // 4, 128, 128), ws.xi0, 128)
+        ws.s0.copy_(e_tile[:, 31, :])
+        _lib.linear(ws.s0, relay.wq.kernel.detach(), None, out=ws.q0, prec=PREC)
+        ws.xi1 = None
+        if first_sat:
+            # one cycle without target keys: rows 0..30 of the result are X' = relu(ATT @ Wo + b) of cycle 0
+            _lib.star_cycles_tc(ws.xi0, ws.s0, ws.q0, ws.kvei, None, 0, sat._packed("qkv_grouped"),
+                                sat.dense.kernel.detach(), relay._packed("kv"), relay.dense.kernel.detach(),
+                                relay.wq.kernel.detach(), sat.dense.bias.detach(), relay.dense.bias.detach(),
+                                ws.x, S, 1, PREC)
+            if ws.xi1_buf is None:
+                ws.xi1_buf = torch.empty((S * 4096,), **f)
+            ws.xi1 = _lib.star_interleave(ws.x.view(S // 4, 128, 128), ws.xi1_buf, 128)
 
 
 def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_num: int,
@@ -326,16 +338,25 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
     gathered by index.  e_tile [S,32,128] with row 31 = mean over tokens; returns the tile after
     ``cycle_num`` cycles (rows 0..30 = h, row 31 = s).  kv2 [S, rows, 256] holds k|v of h2 under the
     relay weights (decoder only), of which the first n2 rows are attended; ``kv2i`` is the same cache
-    already in the interleaved layout of the tcgen05 kernels.  ``relay_row=False``: the caller reads rows 0..30 only
-    (a greedy decoder), so the one-launch kernel skips the relay half of the last cycle (row 31 is then the relay node before its last update)."""
+    already in the interleaved layout of the tcgen05 kernel.  ``relay_row=False``: the caller reads rows 0..30 only
+    (a greedy decoder), so the kernel skips the relay half of the last cycle (row 31 is then the relay node before its
+    last update).
+
+    One launch of dsc_star_cycles_tc runs all cycles (PREC 1 / 2).  PREC 0 (fp32 debug mode) runs the per-op fp32 kernels
+    that the backward tape differentiates."""
     S = e_tile.shape[0]
     if _DIFF:
         return _star_cycles_diff(e_tile, sat, relay, cycle_num, kv2, n2)
-    if ws is None:
-        ws = StarWorkspace(S, e_tile.device)
-    if not kv_e_ready:
-        prepare_kv_e(e_tile, sat, ws, relay)
-    if use_tc(S) and STAR_FUSED:
+    if use_tc():
+        if S % 4:                                       # ragged batch: pad to whole tiles, drop the padding again
+            assert ws is None and not kv_e_ready and kv2i is None
+            x = star_cycles(_pad4(e_tile), sat, relay, cycle_num, None if kv2 is None else _pad4(kv2), n2,
+                            relay_row=relay_row)
+            return x[:S]
+        if ws is None:
+            ws = StarWorkspace(S, e_tile.device)
+        if not kv_e_ready:
+            prepare_kv_e(e_tile, sat, ws, relay)
         if n2 > 0 and kv2i is None:
             pad = torch.zeros((S, 32, 256), device=e_tile.device, dtype=torch.float32)
             pad[:, : kv2.shape[1]] = kv2
@@ -346,27 +367,10 @@ def star_cycles(e_tile: torch.Tensor, sat: sublayer1, relay: sublayer1, cycle_nu
                                    relay.wq.kernel.detach(), sat.dense.bias.detach(), relay.dense.bias.detach(),
                                    ws.x, S, cycle_num, PREC | (_lib.STAR_FIRST_SAT_DONE if skip else 0)
                                    | (0 if relay_row else _lib.STAR_NO_FINAL_RELAY))
-    if use_tc(S):
-        # tcgen05 path: two fused persistent kernels per cycle (projection + satellite attention; dense + relay
-        # k|v projection + relay attention) plus the two per-sentence Dense calls of the relay node.
-        if n2 > 0 and kv2i is None:
-            pad = torch.zeros((S, 32, 256), device=e_tile.device, dtype=torch.float32)
-            pad[:, : kv2.shape[1]] = kv2
-            kv2i = _lib.star_interleave(pad, torch.empty_like(pad).view(-1), 32)
-        w_g, wo, bo = sat._packed("qkv_grouped"), sat.dense.kernel.detach(), sat.dense.bias.detach()
-        wkv_r, wq_r = relay._packed("kv"), relay.wq.kernel.detach()
-        wo_r, bo_r = relay.dense.kernel.detach(), relay.dense.bias.detach()
-        xi, atti = ws.qkv.view(-1)[: S * 4096], ws.att.view(-1)           # reuse the unfused path's scratch
-        _lib.star_interleave(e_tile.view(S // 4, 128, 128), xi, 128)
-        ws.s_buf.copy_(e_tile[:, 31, :])
-        _lib.linear(ws.s_buf, wq_r, None, out=ws.q_r, prec=PREC)
-        for c in range(cycle_num):
-            last = c + 1 == cycle_num
-            _lib.star_sat_tc(xi, ws.s_buf, ws.kvei, w_g, atti, S, PREC)
-            _lib.star_mix_tc(atti, xi, ws.x if last else None, ws.s_buf, wo, bo, wkv_r, ws.q_r, kv2i, n2, ws.att_r, S, PREC)
-            _lib.star_relay_update(ws.att_r, wo_r, bo_r, wq_r, ws.s_buf, ws.q_r)
-        ws.x[:, 31, :].copy_(ws.s_buf)
-        return ws.x
+    if ws is None:
+        ws = StarWorkspace(S, e_tile.device)
+    if not kv_e_ready:
+        prepare_kv_e(e_tile, sat, ws, relay)
     x2 = ws.x.view(S * 32, 128)
     ws.x.copy_(e_tile)
     s_rows = ws.x[:, 31, :]

@@ -87,7 +87,7 @@ def gather_counts(counts: torch.Tensor, group=None) -> torch.Tensor:
 
 def evaluate_sweep(runner, units: torch.Tensor, snr_points: Sequence[float] = SNR_POINTS, *, channel: str = "AWGN", K: int = 0,
                    rank: int = 0, world: int = 1, group=None, h_seed: int = 7,
-                   weight_sets=((1, 0, 0, 0), (0.25, 0.25, 0.25, 0.25))):
+                   weight_sets=((1, 0, 0, 0), (0.25, 0.25, 0.25, 0.25)), noise_for_item=None, h_all=None):
     """The reference's missing SNR-sweep driver: every 64-sentence unit of ``units``
     [n_units*64, 31] at every SNR point -> greedy ids -> BLEU counts -> rows ``[snr_idx, mean score per weight set...]``
     in the layout of the reference's log/eval-D-GAN-STAR/*.pkl.
@@ -96,6 +96,9 @@ def evaluate_sweep(runner, units: torch.Tensor, snr_points: Sequence[float] = SN
     anything with ``U``, ``dev`` and ``run(inp, n_std, h=...) -> (ids, counts)``) evaluates ``runner.U`` items per call,
     the ragged tail being padded with repeats that are dropped again.  The only exchange is the final gather of the
     int32 count table; float BLEU is formed from the gathered table in fp64, so it does not depend on ``world``.
+    Injected randomness (parity tests): ``noise_for_item(i)`` -> unit-normal [64,31,16] host tensor for global work item
+    ``i`` (default: the runner's on-device Philox stream); ``h_all`` [n_items, 2] fading coefficients (default: drawn
+    from ``h_seed``).
     Returns (rows, counts [n_items*64, 10] int32 on the host, snr index per sentence)."""
     import torch.distributed as dist
     n_units = units.shape[0] // 64
@@ -104,7 +107,10 @@ def evaluate_sweep(runner, units: torch.Tensor, snr_points: Sequence[float] = SN
     mine = items[lo:hi]
     U, dev = runner.U, runner.dev
     gen = torch.Generator().manual_seed(h_seed)
-    h_all = fading_coefficients(K, len(items), gen) if channel != "AWGN" else None   # indexed by global item id
+    if channel == "AWGN":
+        h_all = None
+    elif h_all is None:
+        h_all = fading_coefficients(K, len(items), gen)                              # indexed by global item id
     out = torch.zeros((len(mine) * 64, 10), dtype=torch.int32)
     for b0 in range(0, len(mine), U):
         blk = mine[b0:b0 + U]
@@ -112,10 +118,13 @@ def evaluate_sweep(runner, units: torch.Tensor, snr_points: Sequence[float] = SN
         inp = torch.cat([units[64 * u:64 * u + 64] for _, u in pad], dim=0).to(dev)
         n_std = torch.tensor([snr_to_noise(snr_points[s]) for s, _ in pad], dtype=torch.float32, device=dev)
         h = None
+        idx = [lo + b0 + min(j, len(blk) - 1) for j in range(U)]
         if h_all is not None:
-            idx = [lo + b0 + min(j, len(blk) - 1) for j in range(U)]
             h = h_all[idx].to(dev).contiguous()
-        _, counts = runner.run(inp, n_std, h=h)
+        if noise_for_item is not None:
+            _, counts = runner.run(inp, n_std, h=h, noise=torch.cat([noise_for_item(i) for i in idx]).to(dev))
+        else:
+            _, counts = runner.run(inp, n_std, h=h)
         out[b0 * 64:(b0 + len(blk)) * 64] = counts[: len(blk) * 64].to("cpu", torch.int32)
     if world > 1 and dist.is_available() and dist.is_initialized():
         # ragged shards: pad to the largest block, gather, trim

@@ -59,14 +59,18 @@ def _call(net, inp, tar_inp, p, PNR_dB, channel, n_std, masks, **kw):
                combined_mask=combined_mask, dec_padding_mask=dec_padding_mask, **kw)
 
 
-def _symbol_gradient(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks, noise, h, gan=False, wrt="symbols"):
-    """First (clean) forward under the tape and d(loss)/d(symbols).  Returns (loss, predictions, gradient, outs)."""
+def _symbol_gradient(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks, noise, h, gan=False, wrt="symbols",
+                     reforward_awgn=True):
+    """First (clean) forward under the tape and d(loss)/d(symbols or received symbols).  ``reforward_awgn``: over a fading
+    channel the eval_step_* functions take the direction from a second, AWGN forward (utlis/eval.py:204-211); the greedy
+    decoders differentiate the forward of the given channel itself (:25-33, :137-144).
+    Returns (loss, predictions, gradient, outs)."""
     with _frozen(net), differentiable():
         kw = dict(noise_r=noise, h_r=h, traingan=False) if gan else dict(noise=noise, h=h)
         outs = _call(net, inp, tar_inp, None, PNR_dB, channel, n_std, masks, **kw)
         pred = outs[1] if gan else outs[0]
         loss = loss_function(tar_real, pred)
-        if channel != 'AWGN':
+        if channel != 'AWGN' and reforward_awgn:
             # the attack direction is taken through an AWGN forward (utlis/eval.py:204-211, 336-344, 384-390)
             kw2 = dict(noise_r=noise, traingan=False) if gan else dict(noise=noise)
             outs2 = _call(net, inp, tar_inp, None, PNR_dB, 'AWGN', n_std, masks, **kw2)
@@ -177,15 +181,25 @@ def _pgd_first(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks, noise
     return loss.detach(), outs[0].detach(), g, None
 
 
+def _draw(net, seed):
+    """(seed, offset) of the on-device Philox stream for one channel call: every call advances the channel layer's
+    counter, so successive batches and SNR points see fresh noise, as tf.random.normal gives the reference
+    (utlis/eval.py:90-93).  ``seed`` overrides the layer's seed when given."""
+    layer = net.channel_layer
+    return (layer.seed if seed is None else seed), layer._next_offset()
+
+
 def greedy_decode_noattack(args, inp, net, PNR_dB, channel='AWGN', n_std=0.1, epsilon=1, *, noise=None, h=None,
-                           seed: int = 0, decoder=None):
+                           seed=None, decoder=None):
     """utlis/eval.py:78-117.  ``noise`` = injected unit-normal tensor [bs,31,16]; ``h`` = the two
     unit-normal draws of the fading coefficient (z1, z2).  AWGN is the inline form without sqrt(size)
-    (:90-93); p is zero so PNR_dB has no effect, as in the reference."""
+    (:90-93); p is zero so PNR_dB has no effect, as in the reference.  Without ``noise`` every call draws a fresh
+    Philox sample (``net.channel_layer`` holds the seed and the call counter)."""
     dev = inp.device
     ns = torch.full((1,), float(n_std), device=dev, dtype=torch.float32)
+    sd, off = _draw(net, seed)
     out = engine.greedy_units(net, inp, 1, ns, channel=channel, noise=None if noise is None else noise.contiguous(),
-                              seed=seed, h=_fading_h(channel, h, dev), max_length=args.max_length,
+                              seed=sd, offset=off, h=_fading_h(channel, h, dev), max_length=args.max_length,
                               start_idx=args.start_idx, decoder=decoder)
     return out.clone()
 
@@ -197,8 +211,9 @@ def _attacked_greedy(args, inp, net, PNR_dB, channel, n_std, pertutation, noise,
     PNR = 10 ** (PNR_dB / 10)
     ps = torch.full((1,), float(n_std) * math.sqrt(PNR), device=dev, dtype=torch.float32)
     inp32 = inp.to(torch.int32).contiguous()
+    sd, off = _draw(net, seed)
     x, y = engine.transmit(net, inp32, 1, ns, channel=channel, noise=None if noise is None else noise.contiguous(),
-                           seed=seed, h=_fading_h(channel, h, dev), p=pertutation if channel == 'AWGN' else None,
+                           seed=sd, offset=off, h=_fading_h(channel, h, dev), p=pertutation if channel == 'AWGN' else None,
                            p_scale=ps if channel == 'AWGN' else None, want_x_norm=True)
     if decoder is None:
         decoder = engine.make_decoder(net, inp32.shape[0], args.max_length, graph=False)
@@ -212,7 +227,7 @@ def _attacked_greedy(args, inp, net, PNR_dB, channel, n_std, pertutation, noise,
 
 
 def greedy_decode(args, inp, net, PNR_dB, channel='AWGN', n_std=0.1, epsilon=1, *, noise=None, noise2=None, h=None,
-                  seed: int = 0, decoder=None):
+                  seed=None, decoder=None):
     """utlis/eval.py:11-75: FGM direction from one teacher-forced pass (gradient w.r.t. the received symbols,
     :25-33), then greedy decoding of the attacked transmission.  Returns (outputs, scaled perturbation,
     channel noise sample, channel_enc_output) like the reference; the third item is the noise realised by the
@@ -221,20 +236,21 @@ def greedy_decode(args, inp, net, PNR_dB, channel='AWGN', n_std=0.1, epsilon=1, 
     star = isinstance(net.semantic_decoder, (M.SD, M.SDecoder))
     tar_real = inp if star else inp[:, 1:]                          # star decoders emit 31 positions (D11)
     masks = create_masks(inp, tar_inp)
-    _, _, g, _ = _symbol_gradient(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks, noise, h, wrt="received")
+    _, _, g, _ = _symbol_gradient(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks, noise, h, wrt="received",
+                                  reforward_awgn=False)
     pertutation = fgm_perturbation(g, epsilon)
     return _attacked_greedy(args, inp, net, PNR_dB, channel, n_std, pertutation, noise2, h, seed, decoder)
 
 
 def greedy_decode_gan(args, inp, net, PNR_dB, channel='AWGN', n_std=0.1, epsilon=1, *, noise=None, noise2=None,
-                      h=None, seed: int = 0, decoder=None):
+                      h=None, seed=None, decoder=None):
     """utlis/eval.py:120-187 (``Transeiver_GAN``): as greedy_decode with the clean branch as the attacked loss;
     additionally returns ``noa`` = teacher-forced argmax of the clean branch (:185).
     Returns (outputs, noa, scaled perturbation, noise sample, channel_enc_output)."""
     tar_inp, tar_real = inp[:, :-1], inp[:, 1:]
     masks = create_masks(inp, tar_inp)
     _, pred_r, g, _ = _symbol_gradient(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks, noise, h, gan=True,
-                                       wrt="received")
+                                       wrt="received", reforward_awgn=False)
     noa = _lib.argmax_rows(pred_r)
     pertutation = fgm_perturbation(g, epsilon)
     outputs, scaled, z, x = _attacked_greedy(args, inp, net, PNR_dB, channel, n_std, pertutation, noise2, h, seed, decoder)

@@ -4,7 +4,10 @@ One forward of ``Transeiver_GAN`` under the tape, then the reference's three opt
   A (:24-29)  loss   = CE(clean branch)                          on every variable except the generator ``g``;
   B (:35-37)  g_loss = 10 - CE(perturbed branch)                  on the generator (trainable_variables[104:108]);
   C (:39-44)  d_loss = l*CE(clean) + (1-l)*CE(perturbed)          on the receiver (channel decoder + semantic decoder;
-              'g', 'encoder', 'channel_encoder' frozen - intent per SURVEY.md App. B Q14).
+              'g', 'encoder', 'channel_encoder' frozen - intent per SURVEY.md App. B Q14).  The reference freezes by
+              ``layer.name`` (:41), and Keras auto-names a ``Channel_Encoder`` instance 'channel__encoder', so as written
+              its channel encoder is NOT frozen in step C; ``step_c_literal_names=True`` reproduces that (step C then also
+              updates the channel encoder with d_loss).  The default follows the stated intent.
 All three gradients are taken at the pre-update weights (one persistent tape), and all three losses are linear in
 CE_r and CE_p, so two backward sweeps fill two flat gradient buffers (d CE_r, d CE_p); with a process group the two
 buffers are all-reduced together in ONE NCCL collective, and the lambda mix of step C is folded into the Adam kernel.
@@ -28,8 +31,12 @@ def _is_receiver(name: str) -> bool:
     return name.startswith("channel_decoder.") or name.startswith("semantic_decoder.")
 
 
+def _is_channel_encoder(name: str) -> bool:
+    return name.startswith("channel_encoder.")
+
+
 def gan_train_step(inp, tar, p, net, optim_net, lenmda, channel='AWGN', n_std=0.1, training=False, traingan=False, *,
-                   noise=None, noise_r=None, h=None, h_r=None, p_draw=None):
+                   noise=None, noise_r=None, h=None, h_r=None, p_draw=None, step_c_literal_names: bool = False):
     """utlis/gan_train.py:8-50.  ``p`` is overwritten as in the reference (:13-14): a normal draw of std n_std
     normalised to unit Frobenius norm (``p_draw`` = injected unit-normal tensor; used only when traingan=False).
     The forward always runs with training=True and PNR_dB = 40 (:16-18).  Returns (loss, g_loss, d_loss)."""
@@ -54,13 +61,14 @@ def gan_train_step(inp, tar, p, net, optim_net, lenmda, channel='AWGN', n_std=0.
         fp.point_grads(0)
         ce_r.backward(inputs=not_g, retain_graph=True)                       # d CE_r / d (everything but g)
         fp.point_grads(1)
-        wanted = fp.select(lambda n: _is_receiver(n) or (traingan and _is_generator(n)))
-        ce_p.backward(inputs=wanted)                                         # d CE_p / d (receiver, generator)
+        step_c = (lambda n: _is_receiver(n) or _is_channel_encoder(n)) if step_c_literal_names else _is_receiver
+        wanted = fp.select(lambda n: step_c(n) or (traingan and _is_generator(n)))
+        ce_p.backward(inputs=wanted)                                         # d CE_p / d (step-C variables, generator)
     scale = O.all_reduce_mean_scale(fp.grad_bucket)
     g_r, g_p = fp.grad_bucket[0], fp.grad_bucket[1]
     optim_net.apply(fp.ranges(lambda n: not _is_generator(n)), g_r, scale)                      # step A
     optim_net.apply(fp.ranges(_is_generator), g_p, -scale)                                      # step B: 10 - CE_p
-    optim_net.apply(fp.ranges(_is_receiver), g_r, scale * float(lenmda), g_p, scale * (1.0 - float(lenmda)))   # step C
+    optim_net.apply(fp.ranges(step_c), g_r, scale * float(lenmda), g_p, scale * (1.0 - float(lenmda)))          # step C
     loss = ce_r.detach()
     return loss, 10 - ce_p.detach(), float(lenmda) * loss + (1 - float(lenmda)) * ce_p.detach()
 
@@ -89,6 +97,10 @@ class GraphedGanTrainStep:
     """
 
     def __init__(self, net, optim_net, lenmda, channel='AWGN', n_std=0.1, traingan=True, warmup: int = 2):
+        if channel != 'AWGN':
+            # Channels.fading draws its coefficient on the host (models/transceiver.py:48-50 is one scalar per call): a
+            # capture would bake ONE coefficient into every replay.  Use the eager gan_train_step for fading channels.
+            raise ValueError("GraphedGanTrainStep supports channel='AWGN' only; call gan_train_step for fading channels")
         self.net, self.opt, self.lenmda, self.channel, self.n_std, self.traingan = net, optim_net, lenmda, channel, n_std, traingan
         self.warmup, self.graph, self.out = warmup, None, None
         dev = optim_net.fp.flat.device
@@ -101,7 +113,7 @@ class GraphedGanTrainStep:
         z = torch.randn(shape, device=dev)
         z_r = torch.randn(shape, device=dev)
         p_draw = torch.randn(shape, device=dev)
-        return gan_train_step(self._inp, self._inp, None, self.net, self.opt, self.lenmda, channel=self.channel,
+        return gan_train_step(self._inp, self._tar, None, self.net, self.opt, self.lenmda, channel=self.channel,
                               n_std=self.n_std, training=True, traingan=self.traingan, noise=z, noise_r=z_r, p_draw=p_draw)
 
     def __call__(self, inp, tar=None):
@@ -110,6 +122,7 @@ class GraphedGanTrainStep:
         try:
             if self.graph is None:
                 self._inp = inp.clone()
+                self._tar = self._inp if (tar is None or tar is inp) else tar.clone()   # the dataset yields (x, x)
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(side):
@@ -126,6 +139,10 @@ class GraphedGanTrainStep:
             else:
                 self.opt.iterations += 3
             self._inp.copy_(inp)
+            if self._tar is not self._inp:
+                self._tar.copy_(inp if tar is None else tar)
+            elif tar is not None and tar is not inp:
+                raise ValueError("this step was captured with tar = inp; build another GraphedGanTrainStep for a separate target")
             self.graph.replay()
             self.steps += 1
             _lib.weights_changed()                                 # packed / padded weight caches of eager callers

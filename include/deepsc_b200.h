@@ -92,38 +92,20 @@ int dsc_star_pack(const float* src, float* tile, int n_sent, void* stream);
  * {h[i+1], h[i], h[i-1], e[i], s} (cyclic neighbours, no mask); row 31 is zero-filled. */
 int dsc_star_satellite_attn(const float* qkv, const float* kv_e, float* att, int n_sent, void* stream);
 
-/* Fused tcgen05 star-cycle kernels (persistent CTAs, weights resident in shared memory, operand staged in TMEM).
- * They stream per-row data in the "interleaved tile" layout [tile][k/4][row][4 floats] (a tile = 4 sentences = 128
- * rows = 128 TMEM lanes) so that a warp's 32 rows read 512 contiguous bytes; dsc_star_interleave converts a
- * row-major [n_groups*group_rows, width] tensor (group_rows 128, or 32 for the h2 cache) into it.  The relay node of
- * each sentence lives in a compact buffer s_relay [n_sent,128] (row 31 of a tile is not stored).  n_sent % 4 == 0.
- * prec 1 = bf16x3, 2 = bf16. */
+/* The fused tcgen05 star-cycle kernel (dsc_star_cycles_tc below) reads per-row data in the "interleaved tile" layout
+ * [tile][k/4][row][4 floats] (a tile = 4 sentences = 128 rows = 128 TMEM lanes), so that a warp's 32 rows read 512
+ * contiguous bytes; dsc_star_interleave converts a row-major [n_groups*group_rows, width] tensor (group_rows 128, or
+ * 32 for the h2 key cache) into it.  n_sent % 4 == 0. */
 int dsc_star_interleave(const float* src, int64_t src_group_stride, float* dst, int n_groups, int group_rows,
                         int width, void* stream);
 /* vals [n_sent,256] (k|v of one h2 row per sentence) -> row `row_index` of kv2 [n_sent][64][32][4]. */
 int dsc_star_kv2_put(const float* vals, float* kv2, int row_index, int n_sent, void* stream);
 
-/* K2+K3: att = satellite_attention(x @ [wq|wk|wv]_satellite, kv_e); the [rows,384] projection stays in TMEM
- * (models/modules.py:289-299).  x_tile, att: [n_sent/4][32][128][4]; kv_e: [n_sent/4][64][128][4] (k|v of the e rows);
- * packed_wqkv_grouped = dsc_pack_weight of the [128,384] matrix whose columns are ordered by head pair g = 0..3:
- * [wq[:,32g:32g+32] | wk[:,32g:32g+32] | wv[:,32g:32g+32]]. */
-int dsc_star_sat_tc(const float* x_tile, const float* s_relay, const float* kv_e, const void* packed_wqkv_grouped,
-                    float* att, int n_sent, int prec, void* stream);
-
-/* K2+K4: x rows 0..30 <- relu(att @ wo_sat + bias_o) (models/modules.py:299), written to x_tile (interleaved) or,
- * when x_rowmajor != NULL, to x_rowmajor [n_sent][32][128] with row 31 = s_relay (last cycle); then
- * k|v = x @ [wk|wv]_relay in TMEM and the relay attention (:303-306, :375-378) of q_relay [n_sent,128] over the 32
- * rows (31 satellites + s) plus the first n2 rows of kv2 [n_sent][64][32][4]; att_relay [n_sent,128] is the output
- * before the relay dense layer.  packed_wo / packed_wkv_relay = dsc_pack_weight of [128,128] / [128,256]. */
-int dsc_star_mix_tc(const float* att, float* x_tile, float* x_rowmajor, const float* s_relay,
-                    const void* packed_wo, const void* packed_wkv_relay,
-                    const float* bias_o, const float* q_relay, const float* kv2, int n2,
-                    float* att_relay, int n_sent, int prec, void* stream);
-
 /* K2+K3+K4, all cycles in one launch: the loop of models/modules.py:287-306 / 360-378 with the tile state (X, ATT, s, q)
  * resident in tensor / shared memory and the weights streamed from L2 through a shared-memory ring.
  * x_tile0 [n_sent/4][32][128][4] = the e tile (cycle-0 node states, interleaved); s0 [n_sent,128] = mean row;
- * q0 [n_sent,128] = s0 @ wq_relay; kv_e, kv2, n2 as in dsc_star_sat_tc / dsc_star_mix_tc; the five packed weights are
+ * q0 [n_sent,128] = s0 @ wq_relay; kv_e [n_sent/4][64][128][4] = k|v of the e rows under the satellite weights (interleaved); kv2 [n_sent][64][32][4] = the cached
+ * k|v of the h2 rows under the relay weights, of which the first n2 rows are attended (decoder only; n2 = 0, kv2 NULL otherwise); the five packed weights are
  * dsc_pack_weight images of the grouped [128,384] satellite projection, wo_satellite, [wk|wv]_relay, wo_relay, wq_relay
  * (pass the satellite matrices again for the layers that drive the relay with the satellite weights, :175, :243).
  * x_rowmajor [n_sent][32][128] receives the tile after n_cycles cycles (rows 0..30 = h, row 31 = s).
@@ -151,11 +133,6 @@ int dsc_target_tail_tc(const float* attn, int64_t ld_attn, const float* resid, i
                        const void* packed_wkv_relay, float* kv2, int row_index,
                        float* kv_rows, int64_t ld_kv, float* h2_out, int64_t ld_h2,
                        int M, int prec, void* stream);
-
-/* relay node update: s_out = relu(att_relay @ wo + bo) (models/modules.py:305-306), q_out = s_out @ wq (the next
- * cycle's relay query).  fp32 FFMA, weights Keras layout [128,128] contiguous, all tensors [n_sent,128]. */
-int dsc_star_relay_update(const float* att_relay, const float* wo, const float* bo, const float* wq,
-                          float* s_out, float* q_out, int n_sent, void* stream);
 
 /* K4: relay attention of one star cycle (models/modules.py:303-306, 375-378).
  * qkv_r [n_sent*32, 384] = updated tile @ [wq|wk|wv] of the relay weights; the query is row 31,
@@ -331,14 +308,6 @@ int dsc_dropout(const float* x, float* out, float rate, uint64_t seed, uint64_t 
 int dsc_adam_step(float* param, const float* grad, const float* grad2, float* m, float* v, float lr, float beta1,
                   float beta2, float eps, int step, const int64_t* step_dev, int steps_per_iter,
                   float grad_scale, float grad2_scale, int64_t n, void* stream);
-
-/* Micro-benchmark (not on the product path): cycles for iters x 8 back-to-back tcgen05.mma (M = 128, K = 16, width n) with
- * the A operand in tensor memory (ts_mode != 0) or shared memory; result in cycles_dev[0]. */
-int dsc_umma_probe(int ts_mode, int n, int iters, long long* cycles_dev, void* stream);
-
-/* Debug timeline of dsc_star_cycles_tc (not on the product path): registers a device buffer of 768 uint64 (NULL = off);
- * CTA 0 of every later launch stamps clock64() at the hand-offs of its first tile (layout: dsc_star_fused.cu). */
-int dsc_debug_star_trace(void* device_buffer_768_u64);
 
 #ifdef __cplusplus
 }

@@ -425,6 +425,202 @@ def eval_step(P: Params, spec: Spec, inp, tar, PNR_dB, channel, n_std, z, z2, h_
 
 
 # --------------------------------------------------------------------------- #
+# attacked evaluators and the adversarial training step (utlis/eval.py, utlis/trainer.py)
+# --------------------------------------------------------------------------- #
+def _taped_forward(P: Params, spec: Spec, inp, tar_inp, p, PNR_dB, channel, n_std, masks, z, h_z=(0.0, 0.0),
+                   z_r=None, h_z_r=(0.0, 0.0), traingan=False):
+    """One Transeiver*.call under a "tape": the channel symbols become a leaf so that d(loss)/d(symbols) and
+    d(loss)/d(received) exist with frozen parameters (tf.GradientTape watches every intermediate, eval.py:25-33)."""
+    with torch.enable_grad():
+        sem = semantic_encoder(P, spec, inp, masks[0])
+        x = channel_encoder(P, sem).detach().requires_grad_(True)
+        outs = transceiver_forward(P, spec, inp, tar_inp, p, PNR_dB, channel, n_std, *masks, z=z, h_z=h_z, z_r=z_r,
+                                   h_z_r=h_z_r, traingan=traingan, symbols_override=x)
+    return x, outs
+
+
+def _inline_attacked_channel(x, pert, PNR_dB, channel, n_std, z, h_z):
+    """The transmit side of greedy_decode / greedy_decode_gan after the FGM stage, eval.py:47-55 / 157-165: inline AWGN
+    WITHOUT the sqrt(size) factor; the fading branches ignore the perturbation (they pass p = zeros)."""
+    if channel == "AWGN":
+        return awgn(x, pert, PNR_dB, n_std, z, scale_by_sqrt_size=False)
+    return fading(x, 1 if channel == "Rician" else 0, n_std, h_z, z)
+
+
+def _greedy_loop(P: Params, spec: Spec, inp, y, max_length: int, start_idx: int, return_logits: bool = False):
+    """The decoding loop shared by the three greedy functions (eval.py:57-73, 99-115, 167-183)."""
+    outputs = torch.full((inp.shape[0], 1), start_idx, dtype=torch.int64)
+    enc_padding_mask = create_padding_mask(inp)
+    step_logits = []
+    for _ in range(max_length):
+        combined = torch.maximum(create_padding_mask(outputs), create_look_ahead_mask(outputs.shape[1]))
+        mem = channel_decoder(P, y)
+        pred = semantic_decoder(P, spec, outputs, mem, combined, enc_padding_mask, last_only=True)
+        if return_logits:
+            step_logits.append(pred[:, -1, :].clone())
+        outputs = torch.cat([outputs, torch.argmax(pred[:, -1:, :], dim=-1)], dim=-1)
+    if return_logits:
+        return outputs.to(torch.int32), torch.stack(step_logits, dim=1)
+    return outputs.to(torch.int32)
+
+
+def greedy_decode(P: Params, spec: Spec, inp, PNR_dB, channel, n_std, z, z2, h_z=(0.0, 0.0), epsilon: float = 1.0,
+                  max_length: int = 30, start_idx: int = 1):
+    """utlis/eval.py:11-75 (evaluation under the FGM attack).  One teacher-forced pass under the tape with p = 0
+    (:25-29, channel draw ``z``), gradient of the loss with respect to the RECEIVED symbols y (:33), per-sample /
+    global normalisation (:36-44), attacked transmission with a fresh draw ``z2`` (:48-55), greedy loop.
+    The reference's target is inp[:, 1:] (:21), which only fits the baseline decoder; the star decoders emit 31
+    positions (D11) and take the full ``inp`` as eval_step_star does (:334).
+    Returns (outputs, n_std*sqrt(PNR)*perturbation, symbols x)."""
+    tar_inp = inp[:, :-1]
+    tar_real = inp if spec.is_star else inp[:, 1:]
+    masks = create_masks(inp, tar_inp)
+    x, outs = _taped_forward(P, spec, inp, tar_inp, torch.zeros(inp.shape[0], inp.shape[1], 16), PNR_dB, channel,
+                             n_std, masks, z, h_z)
+    with torch.enable_grad():
+        loss = loss_function(tar_real, outs[0])
+        (g,) = torch.autograd.grad(loss, outs[3])
+    pert = fgm_normalize(g, epsilon)
+    with torch.no_grad():
+        y = _inline_attacked_channel(x.detach(), pert, PNR_dB, channel, n_std, z2, h_z)
+        outputs = _greedy_loop(P, spec, inp, y, max_length, start_idx)
+    scaled = float(np.float32(n_std)) * math.sqrt(10 ** (PNR_dB / 10)) * pert
+    return outputs, scaled, x.detach()
+
+
+def greedy_decode_gan(P: Params, spec: Spec, inp, PNR_dB, channel, n_std, z, z2, h_z=(0.0, 0.0), epsilon: float = 1.0,
+                      max_length: int = 30, start_idx: int = 1):
+    """utlis/eval.py:120-187 (``Transeiver_GAN``, traingan left at its default False): the clean branch gives the loss
+    (:141) and the FGM direction w.r.t. y_r (:144); ``noa`` = teacher-forced argmax of the clean branch (:185).
+    The reference unpacks three of the model's four outputs (:138, stale); y_r is the last one.
+    ``z`` is the draw of the clean branch of the teacher-forced pass (the perturbed branch carries p = 0 and its own
+    draw, which no result depends on).  Returns (outputs, noa, scaled perturbation, symbols x)."""
+    assert spec.kind == "Transeiver_GAN"
+    tar_inp, tar_real = inp[:, :-1], inp[:, 1:]
+    masks = create_masks(inp, tar_inp)
+    x, outs = _taped_forward(P, spec, inp, tar_inp, torch.zeros(inp.shape[0], inp.shape[1], 16), PNR_dB, channel,
+                             n_std, masks, z, h_z, z_r=z, h_z_r=h_z, traingan=False)
+    with torch.enable_grad():
+        loss = loss_function(tar_real, outs[1])
+        (g,) = torch.autograd.grad(loss, outs[3])
+    pert = fgm_normalize(g, epsilon)
+    with torch.no_grad():
+        noa = torch.argmax(outs[1], dim=-1).to(torch.int32)
+        y = _inline_attacked_channel(x.detach(), pert, PNR_dB, channel, n_std, z2, h_z)
+        outputs = _greedy_loop(P, spec, inp, y, max_length, start_idx)
+    scaled = float(np.float32(n_std)) * math.sqrt(10 ** (PNR_dB / 10)) * pert
+    return outputs, noa, scaled, x.detach()
+
+
+def eval_step_FGM(P: Params, spec: Spec, inp, tar, PNR_dB, channel, n_std, z, z2, z2_r, h_z=(0.0, 0.0),
+                  epsilon: float = 1.0):
+    """utlis/eval.py:367-408 (``Transeiver_GAN``, traingan=False).  Clean-branch loss (:380); AWGN: direction w.r.t. the
+    received symbols y_r (:390); other channels: an AWGN forward and the direction w.r.t. its channel symbols (:383-388);
+    second forward with the perturbation, scored on the PERTURBED branch (:403-406).  ``z`` = clean-branch draw of the
+    first pass, ``z2`` / ``z2_r`` = perturbed / clean draws of the second.
+    Returns (loss, loss_m, predictions_r, predictions_p_m, perturbation)."""
+    assert spec.kind == "Transeiver_GAN"
+    tar_inp, tar_real = tar[:, :-1], tar[:, 1:]
+    masks = create_masks(inp, tar_inp)
+    zeros = torch.zeros(inp.shape[0], inp.shape[1], 16)
+    x, outs = _taped_forward(P, spec, inp, tar_inp, zeros, PNR_dB, channel, n_std, masks, z, h_z, z_r=z, h_z_r=h_z)
+    with torch.enable_grad():
+        loss = loss_function(tar_real, outs[1])
+        if channel == "AWGN":
+            (g,) = torch.autograd.grad(loss, outs[3])
+        else:
+            x2, outs2 = _taped_forward(P, spec, inp, tar_inp, zeros, PNR_dB, "AWGN", n_std, masks, z, z_r=z)
+            (g,) = torch.autograd.grad(loss_function(tar_real, outs2[1]), x2)
+    pert = fgm_normalize(g, epsilon)
+    with torch.no_grad():
+        outs_m = transceiver_forward(P, spec, inp, tar_inp, pert, PNR_dB, channel, n_std, *masks, z=z2, h_z=h_z,
+                                     z_r=z2_r, h_z_r=h_z, traingan=False)
+        loss_m = loss_function(tar_real, outs_m[0])
+    return loss.detach(), loss_m, outs[1].detach(), outs_m[0], pert
+
+
+def eval_step_normal_pgd(P: Params, spec: Spec, inp, tar, PNR_dB, channel, n_std, z, zs: Sequence[torch.Tensor],
+                         h_z=(0.0, 0.0), epsilon: float = 1.0):
+    """utlis/eval.py:235-318: FGM direction w.r.t. the received symbols of the given channel (:251), then ten bisection
+    steps on the attack strength eps in [0, 1] (:262-304): a forward at p = eps * r/power with the inline AWGN that
+    DOES carry sqrt(size) (:277-280; the fading branches ignore p), ``loss_m < loss`` raises the lower bound, otherwise
+    (eps, loss) is recorded and the upper bound drops.  ``zs`` = the ten channel draws of the bisection forwards.
+    Returns (loss_ori, loss_m, predictions, predictions2, epsilon found) with loss_m = the ORIGINAL loss when any step
+    was recorded (att[-1][1], :299, :311) and epsilon = 1 when none was (:307-308)."""
+    tar_inp, tar_real = tar[:, :-1], tar[:, 1:]
+    masks = create_masks(inp, tar_inp)
+    zeros = torch.zeros(inp.shape[0], inp.shape[1], 16)
+    x, outs = _taped_forward(P, spec, inp, tar_inp, zeros, PNR_dB, channel, n_std, masks, z, h_z)
+    with torch.enable_grad():
+        loss = loss_function(tar_real, outs[0])
+        (g,) = torch.autograd.grad(loss, outs[3])
+    direction = fgm_normalize(g, epsilon)                                # r_list / power
+    loss = loss.detach()
+    hi, lo = 1.0, 0.0
+    eps = (hi + lo) / 2
+    att = []
+    x = x.detach()
+    with torch.no_grad():
+        for i in range(10):
+            p = eps * direction
+            if channel == "AWGN":
+                y = awgn(x, p, PNR_dB, n_std, zs[i], scale_by_sqrt_size=True)          # :277-280
+            else:
+                y = fading(x, 1 if channel == "Rician" else 0, n_std, h_z, zs[i])
+            pred2 = semantic_decoder(P, spec, tar_inp, channel_decoder(P, y), masks[1], masks[2])
+            loss_m = loss_function(tar_real, pred2)
+            if float(loss_m - loss) < 0:                                               # :293
+                lo = eps
+            else:
+                att.append((eps, loss))
+                hi = eps
+            eps = (hi + lo) / 2
+    found = 1.0 if not att else att[-1][0]
+    if att:
+        loss_m = att[-1][1]
+    return loss, loss_m, outs[0].detach(), pred2, found
+
+
+def train_attack_step(P: Params, spec: Spec, inp, tar, PNR_dB, channel, n_std, z, z2, h_z=(0.0, 0.0),
+                      epsilon: float = 1.0):
+    """utlis/trainer.py:30-64 with dropout off (the draws of tf.keras.layers.Dropout are not reproducible): forward,
+    gradient of the loss w.r.t. the received symbols y (:44), per-sample then global normalisation (:45-53), second
+    forward with the perturbation through the model's own channel (Channels.awgn, WITH sqrt(size) and PNR_dB),
+    d loss_m / d every parameter (:61).  The loss target is the full ``tar`` (:32, star models).
+    ``P`` must hold leaf tensors with requires_grad=True.  Returns (loss, loss_m, {name: gradient})."""
+    tar_inp, tar_real = tar[:, :-1], tar
+    masks = create_masks(inp, tar_inp)
+    zeros = torch.zeros(inp.shape[0], inp.shape[1], 16)
+    with torch.enable_grad():
+        outs = transceiver_forward(P, spec, inp, tar_inp, zeros, PNR_dB, channel, n_std, *masks, z=z, h_z=h_z)
+        loss = loss_function(tar_real, outs[0])
+        (g,) = torch.autograd.grad(loss, outs[3])
+        r = fgm_normalize(g.detach(), epsilon)
+        outs2 = transceiver_forward(P, spec, inp, tar_inp, r, PNR_dB, channel, n_std, *masks, z=z2, h_z=h_z)
+        loss_m = loss_function(tar_real, outs2[0])
+        names = list(P)
+        grads = torch.autograd.grad(loss_m, [P[n] for n in names], allow_unused=True)
+    return loss.detach(), loss_m.detach(), dict(zip(names, grads))
+
+
+def greedy_generator_attack(P: Params, spec: Spec, inp, snr_db: float, psr_db: float, z, max_length: int = 30,
+                            start_idx: int = 1, return_logits: bool = False):
+    """BASELINE.json configs[3]: ``Transeiver_GAN`` with the generator's perturbation at a fixed perturbation-to-signal
+    ratio, greedy decode.  Transmit side of Transeiver_GAN.call with traingan=True (models/transceiver.py:277-287):
+    p = G(x); the channel is Channels.awgn (:25-33): y = x + n_std*z + n_std*sqrt(PNR)*sqrt(size)*p.  Canonical
+    decision of SURVEY.md App. B Q6: p is normalised to unit Frobenius norm per unit, so sqrt(size)*p has unit mean
+    square and PSR_dB = PNR_dB - SNR_dB."""
+    assert spec.kind == "Transeiver_GAN"
+    n_std = snr_to_noise(snr_db)
+    sem = semantic_encoder(P, spec, inp, create_padding_mask(inp))
+    x = channel_encoder(P, sem)
+    g = generator(P, x)
+    p = g / torch.linalg.vector_norm(g)
+    y = awgn(x, p, snr_db + psr_db, n_std, z, scale_by_sqrt_size=True)
+    return _greedy_loop(P, spec, inp, y, max_length, start_idx, return_logits)
+
+
+# --------------------------------------------------------------------------- #
 # parameter construction (Keras default initialisers restated) and inventory
 # --------------------------------------------------------------------------- #
 def _glorot(gen, fan_in, fan_out):

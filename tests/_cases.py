@@ -17,13 +17,17 @@ NOISE_SEED = 7
 SNR_DB = 6.0
 
 
-def params(kind: str, gain: float = 1.0):
-    """Keras-default init (seed 2024) with perturbed biases / LN affine so every parameter matters."""
+def params(kind: str, gain: float = 1.0, emb_gain: float = 1.0):
+    """Keras-default init (seed 2024) with perturbed biases / LN affine so every parameter matters.  ``gain`` scales the
+    query / key projections (sharper attention), ``emb_gain`` the embedding tables (token identity dominates the
+    positional code): with both > 1 the decoded ids depend on the input sentence the way a trained model's do."""
     P = O.init_params(O.Spec(kind), seed=WEIGHT_SEED, randomize_affine=True)
-    if gain != 1.0:
+    if gain != 1.0 or emb_gain != 1.0:
         for k in P:
             if "/wq/" in k or "/wk/" in k:
                 P[k] = P[k] * gain
+            elif k.endswith("/embedding/embeddings"):
+                P[k] = P[k] * emb_gain
     return P
 
 
@@ -70,3 +74,153 @@ def oracle_case(kind: str, channel: str = "AWGN", unit_index: int = 0, greedy: b
 
 def golden_path(kind: str, channel: str) -> str:
     return os.path.join(GOLDEN_DIR, f"golden_{kind}_{channel}.npz")
+
+
+def max_rel(a, b) -> float:
+    """Element-wise relative error with the tensor's RMS as the absolute floor: max |a - b| / (|b| + rms(b)).  (A purely
+    element-wise |a - b| / |b| is meaningless for logits and symbols that cross zero.)"""
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    rms = float(b.pow(2).mean().sqrt()) + 1e-30
+    return float(((a - b).abs() / (b.abs() + rms)).max())
+
+
+# --------------------------------------------------------------------------- margin-enforced greedy cases
+# name -> (system, channel, first synthetic unit, SNR dB, PSR dB of the generator attack or None, weight variant).
+# Weight variants: "keras" = the seeded Keras initialisation; "lively" = the same with the embeddings x4 and the
+# query / key projections x3, which makes the decoded ids depend on the input (about 170 distinct ids per unit for the
+# baseline decoder instead of about 10), so that an id comparison exercises more than one constant token.
+MARGIN_CASES = {
+    "Transeiver_AWGN": ("Transeiver", "AWGN", 40, 6.0, None, "keras"),                    # BASELINE.json configs[0]
+    "Transeiver_AWGN_lively": ("Transeiver", "AWGN", 50, 6.0, None, "lively"),
+    "Transeiver_Star_AWGN": ("Transeiver_Star", "AWGN", 41, 6.0, None, "keras"),          # configs[1]
+    "Transeiver_Star_AWGN_0dB": ("Transeiver_Star", "AWGN", 45, 0.0, None, "keras"),      # configs[1], the noisiest sweep point
+    "Transeiver_Star_AWGN_12dB": ("Transeiver_Star", "AWGN", 46, 12.0, None, "keras"),
+    "Transeiver_Star_AWGN_18dB": ("Transeiver_Star", "AWGN", 47, 18.0, None, "keras"),    # configs[1], the cleanest sweep point
+    "Transeiver_Star_AWGN_lively": ("Transeiver_Star", "AWGN", 51, 3.0, None, "lively"),
+    "Transeiver_Star_Rayleigh": ("Transeiver_Star", "Rayleigh", 42, 12.0, None, "keras"), # configs[2]
+    "Transeiver_Star_Rayleigh_6dB": ("Transeiver_Star", "Rayleigh", 48, 6.0, None, "keras"),
+    "Transeiver_star_AWGN": ("Transeiver_star", "AWGN", 43, 6.0, None, "keras"),          # the 4-layer star codec
+    "Transeiver_GAN_generator": ("Transeiver_GAN", "AWGN", 44, 9.0, -6.0, "keras"),       # configs[3]: generator attack, PSR -6 dB
+    "Transeiver_GAN_generator_lively": ("Transeiver_GAN", "AWGN", 52, 9.0, -6.0, "lively"),
+}
+
+
+def margin_params(name: str):
+    kind, variant = MARGIN_CASES[name][0], MARGIN_CASES[name][5]
+    return params(kind, gain=3.0, emb_gain=4.0) if variant == "lively" else params(kind)
+
+
+def margin_path(name: str) -> str:
+    return os.path.join(GOLDEN_DIR, f"margin_{name}.npz")
+
+
+def margin_noise(seeds) -> torch.Tensor:
+    """Unit-normal channel draw [64,31,16] of a margin case: sentence slot b draws from its own generator seeds[b]."""
+    return torch.stack([torch.randn(31, 16, generator=torch.Generator().manual_seed(int(sd))) for sd in seeds])
+
+
+def greedy_with_margin(kind: str, P, inp: torch.Tensor, channel: str, snr_db: float, psr_db, seeds, dtype=torch.float32):
+    """Oracle greedy decode -> (ids [n,31] int32, per-sentence minimum over the 30 steps of (top1 - top2) / max|logit|)."""
+    spec = O.Spec(kind)
+    P = O.to_dtype(P, dtype)
+    h_z = draws()[3]
+    z = margin_noise(seeds).to(dtype)
+    with torch.no_grad():
+        if psr_db is not None:
+            ids, lg = O.greedy_generator_attack(P, spec, inp.long(), snr_db, psr_db, z, return_logits=True)
+        else:
+            ids, lg = O.greedy_decode_noattack(P, spec, inp.long(), 0.0, channel, O.snr_to_noise(snr_db), z, h_z,
+                                               return_logits=True)
+    top2 = lg.topk(2, -1).values
+    rel = (top2[..., 0] - top2[..., 1]) / lg.abs().amax(-1)
+    return ids, rel.min(1).values.double()
+
+
+def margin_oracle(name: str, inp: torch.Tensor, seeds, dtype=torch.float32):
+    """Oracle greedy decode of a margin case -> (ids, per-sentence minimum relative top-2 margin)."""
+    kind, channel, _, snr_db, psr_db, _ = MARGIN_CASES[name]
+    return greedy_with_margin(kind, margin_params(name), inp, channel, snr_db, psr_db, seeds, dtype)
+
+
+# The margin-enforced SNR-sweep case (tests/golden/margin_sweep_<channel>.npz): SWEEP_UNITS 64-sentence units at every
+# point of SWEEP_SNRS = SWEEP_UNITS * len(SWEEP_SNRS) work items in the order of sweep.work_items (SNR-major); item i has
+# its own noise seeds [64]; the fading coefficient of every item is draws()[3].
+SWEEP_SNRS = (0.0, 9.0, 18.0)
+SWEEP_UNITS = 2
+SWEEP_FIRST_UNIT = 60
+
+
+def sweep_margin_path(channel: str) -> str:
+    return os.path.join(GOLDEN_DIR, f"margin_sweep_{channel}.npz")
+
+
+def max_rel(a, b) -> float:
+    """Element-wise relative error with the tensor's RMS as the absolute floor: max |a - b| / (|b| + rms(b)).  (A purely
+    element-wise |a - b| / |b| is meaningless for logits and symbols that cross zero.)"""
+    a = torch.as_tensor(a).detach().cpu().double()
+    b = torch.as_tensor(b).detach().cpu().double()
+    rms = float(b.pow(2).mean().sqrt()) + 1e-30
+    return float(((a - b).abs() / (b.abs() + rms)).max())
+
+
+# --------------------------------------------------------------------------- margin-enforced greedy cases
+# name -> (system, channel, first synthetic unit, SNR dB, PSR dB of the generator attack or None, weight variant).
+# Weight variants: "keras" = the seeded Keras initialisation; "lively" = the same with the embeddings x4 and the
+# query / key projections x3, which makes the decoded ids depend on the input (about 170 distinct ids per unit for the
+# baseline decoder instead of about 10), so that an id comparison exercises more than one constant token.
+MARGIN_CASES = {
+    "Transeiver_AWGN": ("Transeiver", "AWGN", 40, 6.0, None, "keras"),                    # BASELINE.json configs[0]
+    "Transeiver_AWGN_lively": ("Transeiver", "AWGN", 50, 6.0, None, "lively"),
+    "Transeiver_Star_AWGN": ("Transeiver_Star", "AWGN", 41, 6.0, None, "keras"),          # configs[1]
+    "Transeiver_Star_AWGN_0dB": ("Transeiver_Star", "AWGN", 45, 0.0, None, "keras"),      # configs[1], the noisiest sweep point
+    "Transeiver_Star_AWGN_12dB": ("Transeiver_Star", "AWGN", 46, 12.0, None, "keras"),
+    "Transeiver_Star_AWGN_18dB": ("Transeiver_Star", "AWGN", 47, 18.0, None, "keras"),    # configs[1], the cleanest sweep point
+    "Transeiver_Star_AWGN_lively": ("Transeiver_Star", "AWGN", 51, 3.0, None, "lively"),
+    "Transeiver_Star_Rayleigh": ("Transeiver_Star", "Rayleigh", 42, 12.0, None, "keras"), # configs[2]
+    "Transeiver_Star_Rayleigh_6dB": ("Transeiver_Star", "Rayleigh", 48, 6.0, None, "keras"),
+    "Transeiver_star_AWGN": ("Transeiver_star", "AWGN", 43, 6.0, None, "keras"),          # the 4-layer star codec
+    "Transeiver_GAN_generator": ("Transeiver_GAN", "AWGN", 44, 9.0, -6.0, "keras"),       # configs[3]: generator attack, PSR -6 dB
+    "Transeiver_GAN_generator_lively": ("Transeiver_GAN", "AWGN", 52, 9.0, -6.0, "lively"),
+}
+
+
+def margin_params(name: str):
+    kind, variant = MARGIN_CASES[name][0], MARGIN_CASES[name][5]
+    return params(kind, gain=3.0, emb_gain=4.0) if variant == "lively" else params(kind)
+
+
+def margin_path(name: str) -> str:
+    return os.path.join(GOLDEN_DIR, f"margin_{name}.npz")
+
+
+def margin_noise(seeds) -> torch.Tensor:
+    """Unit-normal channel draw [64,31,16] of a margin case: sentence slot b draws from its own generator seeds[b]."""
+    return torch.stack([torch.randn(31, 16, generator=torch.Generator().manual_seed(int(sd))) for sd in seeds])
+
+
+def margin_oracle(name: str, inp: torch.Tensor, seeds, dtype=torch.float32):
+    """Oracle greedy decode of a margin case -> (ids [64,31] int32, per-sentence minimum over the 30 steps of
+    (top1 - top2) / max|logit|)."""
+    kind, channel, _, snr_db, psr_db, _ = MARGIN_CASES[name]
+    spec = O.Spec(kind)
+    P = O.to_dtype(margin_params(name), dtype)
+    h_z = draws()[3]
+    z = margin_noise(seeds).to(dtype)
+    with torch.no_grad():
+        if psr_db is not None:
+            ids, lg = O.greedy_generator_attack(P, spec, inp.long(), snr_db, psr_db, z, return_logits=True)
+        else:
+            ids, lg = O.greedy_decode_noattack(P, spec, inp.long(), 0.0, channel, O.snr_to_noise(snr_db), z, h_z,
+                                               return_logits=True)
+    top2 = lg.topk(2, -1).values
+    rel = (top2[..., 0] - top2[..., 1]) / lg.abs().amax(-1)
+    return ids, rel.min(1).values.double()
+
+
+def europarl_test():
+    """The reference's whole test set (tests/golden/make_europarl_fixture.py): (ids [7347,31] int32 padded post,
+    token_to_idx dict of all 22,234 tokens)."""
+    fx = np.load(os.path.join(GOLDEN_DIR, "europarl_test.npz"))
+    tokens = bytes(fx["tokens"]).decode("utf-8").split("\n")
+    return fx["ids"].astype(np.int32), {tok: i for i, tok in enumerate(tokens)}

@@ -22,3 +22,13 @@ def dev():
     from deepsc_gan_b200 import _lib
     _lib.load()            # fail loudly if the extension is missing: no fallback
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _default_precision():
+    """Every test starts and ends in the package's default arithmetic (prec 1, tcgen05 bf16x3); a test that wants the fp32
+    debug mode or the single-pass bf16 mode selects it explicitly."""
+    import deepsc_gan_b200.models.modules as Mod
+    Mod.set_precision(1)
+    yield
+    Mod.set_precision(1)

@@ -367,34 +367,98 @@ def test_fgm_eval_steps_match_oracle(dev):
         assert all(p.requires_grad for p in net.parameters())         # _frozen restores the flags
 
 
-def test_attacked_greedy_and_pgd_run(dev):
-    """greedy_decode (FGM + greedy), greedy_decode_gan, eval_step_FGM, eval_step_normal_pgd: arity, shapes, and
-    consistency with the oracle where the oracle restates them (greedy with an injected perturbation)."""
+def test_fgm_attacked_greedy_decoders_match_oracle(dev):
+    """greedy_decode (utlis/eval.py:11-75) on a star and on the baseline system and greedy_decode_gan (:120-187): the
+    scaled FGM perturbation (hence d loss / d received symbols), the symbols, the realised noise, the teacher-forced
+    clean-branch argmax ``noa`` and the greedy ids against the oracle's restatement of the same functions."""
     from deepsc_gan_b200.utlis import eval as E
     z, z2, _, h_z, _ = _cases.draws()
     n_std = O.snr_to_noise(_cases.SNR_DB)
-    kind = "Transeiver_Star"
-    args, net = build(kind, dev)
     inp = _cases.synthetic_unit(3)
-    outputs, scaled, noise, x = E.greedy_decode(args, inp.to(dev), net, 6.0, channel="AWGN", n_std=n_std, epsilon=1,
-                                                noise=z.to(dev), noise2=z2.to(dev))
-    assert tuple(outputs.shape) == (64, 31) and outputs.dtype == torch.int32
-    assert rel_err(noise, n_std * z2) < 1e-4
-    pert = scaled.cpu() / (n_std * math.sqrt(10 ** 0.6))
-    ref_ids = O.greedy_decode_noattack(_cases.params(kind), O.Spec(kind), inp.long(), 6.0, "AWGN", n_std, z2,
-                                       perturbation=pert)
+    for kind in ("Transeiver_Star", "Transeiver"):
+        args, net = build(kind, dev)
+        outputs, scaled, noise, x = E.greedy_decode(args, inp.to(dev), net, 6.0, channel="AWGN", n_std=n_std, epsilon=1,
+                                                    noise=z.to(dev), noise2=z2.to(dev))
+        ref_ids, ref_scaled, ref_x = O.greedy_decode(_cases.params(kind), O.Spec(kind), inp.long(), 6.0, "AWGN", n_std, z, z2)
+        assert tuple(outputs.shape) == (64, 31) and outputs.dtype == torch.int32
+        assert rel_err(x, ref_x) < 1e-3 and rel_err(noise, n_std * z2) < 1e-3
+        assert rel_err(scaled, ref_scaled) < 2e-3, kind
+        assert (outputs.cpu() == ref_ids).all(1).float().mean() >= 62 / 64, kind
+    # Rayleigh: the fading branch ignores the perturbation (:52-55) but still returns it
+    args, net = build("Transeiver_Star", dev)
+    outputs, scaled, noise, x = E.greedy_decode(args, inp.to(dev), net, 6.0, channel="Rayleigh", n_std=n_std, noise=z.to(dev),
+                                                noise2=z2.to(dev), h=h_z)
+    ref_ids, ref_scaled, _ = O.greedy_decode(_cases.params("Transeiver_Star"), O.Spec("Transeiver_Star"), inp.long(), 6.0,
+                                             "Rayleigh", n_std, z, z2, h_z)
+    assert noise is None and rel_err(scaled, ref_scaled) < 2e-3
     assert (outputs.cpu() == ref_ids).all(1).float().mean() >= 62 / 64
     # GAN model
     args, gan = build("Transeiver_GAN", dev)
+    P, spec = _cases.params("Transeiver_GAN"), O.Spec("Transeiver_GAN")
     out = E.greedy_decode_gan(args, inp.to(dev), gan, 6.0, channel="AWGN", n_std=n_std, noise=z.to(dev), noise2=z2.to(dev))
+    ref = O.greedy_decode_gan(P, spec, inp.long(), 6.0, "AWGN", n_std, z, z2)
     assert len(out) == 5 and tuple(out[0].shape) == (64, 31) and tuple(out[1].shape) == (64, 30)
-    r = E.eval_step_FGM(inp.to(dev), inp.to(dev), gan, 6.0, channel="AWGN", n_std=n_std, noise=z.to(dev), noise2=z2.to(dev),
-                        noise2_r=z.to(dev))
-    assert len(r) == 4 and float(r[1]) >= float(r[0]) - 1e-3          # the attack does not lower the loss
+    assert (out[0].cpu() == ref[0]).all(1).float().mean() >= 62 / 64
+    assert (out[1].cpu() == ref[1]).float().mean() > 0.995                  # noa: teacher-forced argmax of the clean branch
+    assert rel_err(out[2], ref[2]) < 2e-3 and rel_err(out[4], ref[3]) < 1e-3
+
+
+@pytest.mark.parametrize("channel", ["AWGN", "Rayleigh"])
+def test_eval_step_FGM_matches_oracle(dev, channel):
+    """utlis/eval.py:367-408 on ``Transeiver_GAN``: clean-branch loss, direction w.r.t. y_r (AWGN) or w.r.t. the channel
+    symbols of an extra AWGN forward (fading), attacked loss on the perturbed branch, both prediction tensors."""
+    from deepsc_gan_b200.utlis import eval as E
+    z, z2, _, h_z, _ = _cases.draws()
+    n_std = O.snr_to_noise(_cases.SNR_DB)
+    inp = _cases.synthetic_unit(3)
+    args, gan = build("Transeiver_GAN", dev)
+    ref = O.eval_step_FGM(_cases.params("Transeiver_GAN"), O.Spec("Transeiver_GAN"), inp.long(), inp.long(), 6.0, channel,
+                          n_std, z, z2, z, h_z)
+    got = E.eval_step_FGM(inp.to(dev), inp.to(dev), gan, 6.0, channel=channel, n_std=n_std, noise=z.to(dev),
+                          noise2=z2.to(dev), noise2_r=z.to(dev), h=h_z)
+    assert len(got) == 4
+    assert rel_err(got[0], ref[0]) < 1e-4 and rel_err(got[1], ref[1]) < 1e-3
+    assert rel_err(got[2], ref[2]) < 1e-3 and rel_err(got[3], ref[3]) < 1e-3
+    assert all(p.requires_grad for p in gan.parameters())
+
+
+@pytest.mark.parametrize("channel", ["AWGN", "Rayleigh"])
+def test_pgd_bisection_matches_oracle(dev, channel, capsys):
+    """utlis/eval.py:235-318: the device-side bisection takes the same ten decisions as the reference's host loop:
+    same epsilon (printed, :312), same losses and predictions of the first and the tenth forward."""
+    from deepsc_gan_b200.utlis import eval as E
+    z, z2, p_extra, h_z, _ = _cases.draws()
+    g = torch.Generator().manual_seed(77)
+    zs = [torch.randn(64, 31, 16, generator=g) for _ in range(10)]
+    n_std = O.snr_to_noise(_cases.SNR_DB)
+    inp = _cases.synthetic_unit(3)
     args, base = build("Transeiver", dev)
-    r = E.eval_step_normal_pgd(inp.to(dev), inp.to(dev), base, 6.0, channel="AWGN", n_std=n_std, noise=z.to(dev),
-                               noises=[z2.to(dev)] * 10, verbose=False)
-    assert len(r) == 4 and tuple(r[3].shape) == (64, 30, 22234)
+    ref = O.eval_step_normal_pgd(_cases.params("Transeiver"), O.Spec("Transeiver"), inp.long(), inp.long(), 6.0, channel,
+                                 n_std, z, zs, h_z)
+    got = E.eval_step_normal_pgd(inp.to(dev), inp.to(dev), base, 6.0, channel=channel, n_std=n_std, noise=z.to(dev),
+                                 noises=[t.to(dev) for t in zs], h=h_z, verbose=True)
+    printed = capsys.readouterr().out
+    assert len(got) == 4 and tuple(got[3].shape) == (64, 30, 22234)
+    assert abs(float(printed.split("epsilon=")[1].split()[0]) - ref[4]) < 1e-9, (printed, ref[4])
+    assert rel_err(got[0], ref[0]) < 1e-4 and rel_err(got[1], ref[1]) < 1e-3
+    assert rel_err(got[2], ref[2]) < 1e-3 and rel_err(got[3], ref[3]) < 1e-3
+
+
+def test_eval_noise_advances_between_calls(dev):
+    """Without an injected tensor every greedy call draws fresh channel noise (tf.random.normal per call,
+    utlis/eval.py:90-93): the Philox offset advances with the channel layer's call counter."""
+    from deepsc_gan_b200.utlis import eval as E
+    args, net = build("Transeiver_Star", dev)
+    net.load_tf_state_dict(_cases.params("Transeiver_Star", gain=3.0, emb_gain=4.0))
+    inp = _cases.synthetic_unit(3).to(dev)
+    c0 = net.channel_layer._calls
+    a = E.greedy_decode_noattack(args, inp, net, 0.0, "AWGN", O.snr_to_noise(0.0))
+    b = E.greedy_decode_noattack(args, inp, net, 0.0, "AWGN", O.snr_to_noise(0.0))
+    assert net.channel_layer._calls == c0 + 2 and not torch.equal(a, b)
+    c = E.greedy_decode_noattack(args, inp, net, 0.0, "AWGN", O.snr_to_noise(0.0), seed=5)
+    net.channel_layer._calls -= 1
+    d = E.greedy_decode_noattack(args, inp, net, 0.0, "AWGN", O.snr_to_noise(0.0), seed=5)
+    assert torch.equal(c, d)                                          # same (seed, offset): same stream
 
 
 def _keras_adam(p, g, m, v, step, lr=5e-4, b1=0.9, b2=0.98, eps=1e-8):
@@ -506,15 +570,58 @@ def test_baseline_train_step_and_gan_train_step(dev):
     assert n_big > 100000 and n_bad <= 2e-3 * n_big, (n_bad, n_big)
 
 
-def test_training_with_dropout_and_attack_step_run(dev):
-    """training=True applies dropout at the reference's sites (star layers use their constructor default 0.1): the loss
-    changes with the dropout seed, stays finite, and train_attack_step (FGM adversarial training, utlis/trainer.py:30-64)
-    runs end to end and moves the parameters."""
-    import deepsc_gan_b200.models.modules as Mod
+def test_train_attack_step_matches_oracle(dev):
+    """utlis/trainer.py:30-64 (FGM adversarial training) with dropout off: both losses and the Adam update of every
+    parameter against oracle autograd + the Keras Adam formula."""
     from deepsc_gan_b200.utlis import trainer as T
+    kind = "Transeiver_Star"
+    args, net = build(kind, dev, dropout=0.0)
+    opt = T.make_optimizer(net)
+    inp = _cases.synthetic_unit(6)
+    z, z2 = _cases.draws()[0], _cases.draws()[1]
+    n_std = O.snr_to_noise(3.0)
+    P = {k: v.clone().requires_grad_(True) for k, v in _cases.params(kind).items()}
+    loss_ref, loss_m_ref, grads = O.train_attack_step(P, O.Spec(kind), inp.long(), inp.long(), 3.0, "AWGN", n_std, z, z2)
+    loss, loss_m = T.train_attack_step(inp.to(dev), inp.to(dev), None, 3.0, net, opt, channel="AWGN", n_std=n_std,
+                                       noise=z.to(dev), noise2=z2.to(dev))
+    assert rel_err(loss, loss_ref) < 1e-4 and rel_err(loss_m, loss_m_ref) < 1e-3 and opt.iterations == 1
+    n_big = n_bad = 0
+    for name, prm in net.named_parameters():
+        ref, g = P[name.replace(".", "/")].detach(), grads[name.replace(".", "/")]
+        want, _, _ = _keras_adam(ref, g, torch.zeros_like(ref), torch.zeros_like(ref), 1)
+        big = g.abs() > 5e-2 * g.abs().max()
+        n_big += int(big.sum())
+        n_bad += int((((prm.detach().cpu() - ref) - (want - ref)).abs()[big] > 0.05 * 5e-4).sum())
+    assert n_big > 100000 and n_bad <= 2e-3 * n_big, (n_bad, n_big)
+
+
+def test_gan_train_step_literal_layer_names_also_update_the_channel_encoder(dev):
+    """``step_c_literal_names=True``: Keras names a Channel_Encoder instance 'channel__encoder', so the reference's
+    freeze-by-name (utlis/gan_train.py:41) misses it and step C moves the channel encoder too; the default (intent)
+    leaves it to step A alone."""
+    from deepsc_gan_b200.utlis import gan_train as GT
+    n_std = O.snr_to_noise(3.0)
+    z, z_r, p_draw, _, _ = _cases.draws()
+    inp = _cases.synthetic_unit(5).to(dev)
+    res = {}
+    for literal in (False, True):
+        args, gan = build("Transeiver_GAN", dev, dropout=0.0)
+        opt = GT.make_optimizer(gan)
+        GT.gan_train_step(inp, inp, None, gan, opt, 0.5, channel="AWGN", n_std=n_std, training=True, traingan=True,
+                          noise=z.to(dev), noise_r=z_r.to(dev), p_draw=p_draw.to(dev), step_c_literal_names=literal)
+        res[literal] = {n: p.detach().clone() for n, p in gan.named_parameters()}
+    for n in res[False]:
+        same = torch.equal(res[False][n], res[True][n])
+        assert same != n.startswith("channel_encoder."), n
+
+
+def test_training_with_dropout_runs(dev):
+    """training=True applies dropout at the reference's sites (star layers use their constructor default 0.1): the loss
+    changes with the dropout seed and stays finite."""
+    import deepsc_gan_b200.models.modules as Mod
     args, net = build("Transeiver_Star", dev)
     inp = _cases.synthetic_unit(6).to(dev)
-    z, z2 = _cases.draws()[0].to(dev), _cases.draws()[1].to(dev)
+    z = _cases.draws()[0].to(dev)
     n_std = O.snr_to_noise(3.0)
     losses = []
     for seed in (1, 2):
@@ -525,12 +632,6 @@ def test_training_with_dropout_and_attack_step_run(dev):
                        combined_mask=m[1], dec_padding_mask=m[2], noise=z)
             losses.append(float(Mod.loss_function(inp, outs[0])))
     assert all(math.isfinite(v) for v in losses) and abs(losses[0] - losses[1]) > 1e-6
-    opt = T.make_optimizer(net)
-    before = opt.fp.flat.clone()
-    loss, loss_m = T.train_attack_step(inp, inp, None, 3.0, net, opt, channel="AWGN", n_std=n_std, noise=z, noise2=z2)
-    assert math.isfinite(float(loss)) and math.isfinite(float(loss_m)) and opt.iterations == 1
-    moved = (opt.fp.flat - before).abs()
-    assert float(moved.max()) > 1e-5 and float(moved.max()) < 1e-3            # one Adam step of lr 5e-4
 
 
 def test_graph_replayed_gan_train_step(dev):

@@ -44,7 +44,7 @@ def test_linear_fp32(L, dev, M, K, N, act):
     ldw = (N + 127) // 128 * 128
     wd = torch.zeros(K, ldw, device=dev)
     wd[:, :N] = w.to(dev)
-    y = L.linear(x.to(dev), wd, b.to(dev), act=act, n=N)
+    y = L.linear(x.to(dev), wd, b.to(dev), act=act, n=N, prec=0)
     assert y.shape == (M, N)
     assert rel_err(y, ref) < 2e-6
 
@@ -54,13 +54,13 @@ def test_linear_row_skip_and_strided_output(L, dev):
     x = torch.randn(128, 128, generator=g).to(dev)
     w = torch.randn(128, 128, generator=g).to(dev)
     out = torch.full((128, 128), 7.0, device=dev)
-    L.linear(x, w, None, out=out, row_mod=32, row_skip=31)
+    L.linear(x, w, None, out=out, row_mod=32, row_skip=31, prec=0)
     ref = (x.double() @ w.double()).float()
     keep = torch.arange(128, device=dev) % 32 != 31
     assert torch.allclose(out[keep], ref[keep], rtol=1e-5, atol=1e-4)
     assert bool((out[~keep] == 7.0).all())
     tile = torch.zeros((4, 32, 128), device=dev)
-    L.linear(x[:4], w, None, out=tile[:, 31, :])
+    L.linear(x[:4], w, None, out=tile[:, 31, :], prec=0)
     assert torch.allclose(tile[:, 31, :], ref[:4], rtol=1e-5, atol=1e-4) and float(tile[:, :31].abs().max()) == 0.0
 
 
@@ -131,7 +131,7 @@ def test_star_cycle_kernels_match_literal_oracle(L, dev, n2, prec, tol, monkeypa
     kv2 = None
     if n2:
         kv2 = torch.zeros(S, 30, 256, device=dev)
-        kv2[:, :n2] = L.linear(h2.reshape(-1, 128).to(dev), relay._packed("kv"), None).view(S, n2, 256)
+        kv2[:, :n2] = L.linear(h2.reshape(-1, 128).to(dev), relay._packed("kv"), None, prec=prec).view(S, n2, 256)
     x = M.star_cycles(tile, sat, relay, 1, kv2, n2).clone()
     torch.cuda.synchronize()
     assert rel_err(x[:, :31], h_ref) < tol and rel_err(x[:, 31], s_ref) < tol
@@ -412,28 +412,48 @@ def test_linear_tensor_core_row_skip_strided(L, dev):
 
 
 @pytest.mark.parametrize("prec,tol", [(1, 1e-4), (2, 5e-2)])
-@pytest.mark.parametrize("S", [4, 600, 2368])
-def test_star_sat_fused_matches_unfused(L, dev, S, prec, tol):
-    """dsc_star_sat_tc (UMMA projection + shuffle attention on interleaved tiles) == dsc_linear(fp32) +
-    dsc_star_satellite_attn on row-major tiles."""
+@pytest.mark.parametrize("S,n2", [(4, 0), (600, 17), (2368, 30)])
+def test_star_cycles_at_bench_sizes_match_literal_oracle(L, dev, S, n2, prec, tol, monkeypatch):
+    """dsc_star_cycles_tc at one tile, at a size that does not fill the SMs evenly and at bench.py's 592 tiles (4 per SM):
+    two cycles against the literal tf.roll / concat / 5-key form of the oracle (modules.py:289-306), element-wise."""
     import deepsc_gan_b200.models.modules as M
+    monkeypatch.setattr(M, "PREC", prec)
+    P = _cases.params("Transeiver_Star", gain=3.0)
+    pre = "semantic_decoder/dec_layers"
     g = torch.Generator().manual_seed(S)
-    sat = M.sublayer1(128, 8).to(dev)
+    e = torch.randn(S, 31, 128, generator=g)
+    h2 = torch.randn(S, 30, 128, generator=g)[:, :n2] if n2 else None
+    h_ref, s_ref = O._star_cycles(P, pre, e, h2, 2, "multi_att_relay")
+    sat, relay = M.sublayer1(128, 8).to(dev), M.sublayer1(128, 8).to(dev)
     with torch.no_grad():
-        for w in (sat.wq, sat.wk):
-            w.kernel.mul_(3.0)
-    x = torch.randn(S, 32, 128, generator=g).to(dev)
-    kv_e = torch.randn(S * 32, 256, generator=g).to(dev)
-    qkv = L.linear(x.view(S * 32, 128), sat._packed("qkv"), None)
-    ref = torch.empty(S * 32, 128, device=dev)
-    L.star_satellite_attn(qkv, kv_e, ref, S)
-    xi = L.star_interleave(x.view(S // 4, 128, 128), torch.empty(S * 4096, device=dev), 128)
-    kvei = L.star_interleave(kv_e.view(S // 4, 128, 256), torch.empty(S * 8192, device=dev), 128)
-    atti = torch.full((S * 4096,), 5.0, device=dev)
-    L.star_sat_tc(xi, x[:, 31, :].contiguous(), kvei, sat._packed("qkv_grouped"), atti, S, prec)
+        for mod, name in ((sat, "multi_att_satellite"), (relay, "multi_att_relay")):
+            for w in ("wq", "wk", "wv"):
+                getattr(mod, w).kernel.copy_(P[f"{pre}/{name}/{w}/kernel"])
+            mod.dense.kernel.copy_(P[f"{pre}/{name}/dense/kernel"])
+            mod.dense.bias.copy_(P[f"{pre}/{name}/dense/bias"])
+    kv2 = None
+    if n2:
+        kv2 = torch.zeros(S, 30, 256, device=dev)
+        kv2[:, :n2] = L.linear(h2.reshape(-1, 128).to(dev), relay._packed("kv"), None, prec=prec).view(S, n2, 256)
+    x = M.star_cycles(L.star_pack(e.to(dev)), sat, relay, 2, kv2, n2)
     torch.cuda.synchronize()
-    got = atti.view(S // 4, 32, 128, 4).permute(0, 2, 1, 3).reshape(S * 32, 128)      # undo the interleave
-    assert rel_err(got, ref) < tol
+    assert _cases.max_rel(x[:, :31], h_ref) < 4 * tol and _cases.max_rel(x[:, 31], s_ref) < 4 * tol
+
+
+def test_star_cycles_ragged_batch_is_padded_to_whole_tiles(L, dev):
+    """51 sentences (the last batch of the reference's 7,347-sentence test set, dataset/dataloader.py:14) are padded to 52
+    for the tcgen05 kernel and trimmed again: same rows as the 52-sentence call."""
+    import deepsc_gan_b200.models.modules as M
+    torch.manual_seed(5)
+    sat, relay = M.sublayer1(128, 8).to(dev), M.sublayer1(128, 8).to(dev)
+    e = torch.randn(52, 31, 128, device=dev)
+    e[51] = 0
+    kv2 = torch.randn(52, 30, 256, device=dev)
+    kv2[51] = 0
+    full = M.star_cycles(L.star_pack(e), sat, relay, 3, kv2, 9).clone()
+    part = M.star_cycles(L.star_pack(e[:51].contiguous()), sat, relay, 3, kv2[:51].contiguous(), 9)
+    torch.cuda.synchronize()
+    assert part.shape == (51, 32, 128) and torch.equal(part, full[:51])
 
 
 def test_star_interleave_layout(L, dev):

@@ -1,6 +1,8 @@
 """Model-level parity (-m gpu): the nn.Module mirror of models/ and utlis/ against the CPU oracle and the
-frozen goldens, through the C ABI.  Token ids and BLEU counts must be bit-exact; symbols and logits within
-1e-3 relative (the kernels compute in fp32: prec=0)."""
+frozen goldens, through the C ABI.  Token ids and BLEU counts must be bit-exact (asserted with torch.equal on the
+margin-enforced cases of tests/golden/make_margin_cases.py; on the plain seeded cases a differing sentence must be
+explained by a numerical tie in the oracle's own fp64 logits); symbols and logits within 1e-3 relative.
+Every test runs in the package's default arithmetic (prec 1: tcgen05 bf16x3) unless it says otherwise."""
 import numpy as np
 import pytest
 import torch
@@ -18,12 +20,12 @@ def rel_err(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
-def build(kind, dev):
+def build(kind, dev, params=None):
     import deepsc_gan_b200.models as models
     from deepsc_gan_b200.utlis.parameters import para_config
     args = para_config([])
     net = getattr(models, kind)(args).to(dev).eval()
-    net.load_tf_state_dict(_cases.params(kind))
+    net.load_tf_state_dict(_cases.params(kind) if params is None else params)
     return args, net
 
 
@@ -48,9 +50,14 @@ def explained_mismatches(kind, channel, ids_gpu, ids_ref, inp):
     return len(bad), unexplained
 
 
+@pytest.mark.parametrize("prec", [1, 0])
 @pytest.mark.parametrize("kind,channel", [("Transeiver_Star", "AWGN"), ("Transeiver_Star", "Rayleigh"),
                                           ("Transeiver", "AWGN"), ("Transeiver_star", "AWGN"), ("Transeiver_GAN", "AWGN")])
-def test_forward_and_greedy_against_goldens(dev, kind, channel):
+def test_forward_and_greedy_against_goldens(dev, kind, channel, prec, monkeypatch):
+    """Teacher-forced forward (symbols, received symbols, logits, loss) and greedy decode of every system against the
+    frozen oracle outputs, in the default tcgen05 arithmetic (prec 1) and in the fp32 debug mode (prec 0)."""
+    import deepsc_gan_b200.models.modules as M0
+    monkeypatch.setattr(M0, "PREC", prec)
     from deepsc_gan_b200.models.modules import create_masks, loss_function
     from deepsc_gan_b200.utlis.eval import greedy_decode_noattack
     from deepsc_gan_b200.utlis.tools import BleuScore
@@ -70,9 +77,10 @@ def test_forward_and_greedy_against_goldens(dev, kind, channel):
             pred, x, y, y_again = net(inp, tar_inp, p.to(dev), 3.0, channel, n_std, False, *masks, noise=z.to(dev), h=h_z)
             assert y_again is y
     assert tuple(pred.shape) == (64, gold["lse"].shape[1], 22234)
-    assert rel_err(x[:8], gold["symbols"]) < RTOL
-    assert rel_err(y[:8], gold["received"]) < RTOL
+    assert rel_err(x[:8], gold["symbols"]) < RTOL and _cases.max_rel(x[:8], gold["symbols"]) < RTOL
+    assert rel_err(y[:8], gold["received"]) < RTOL and _cases.max_rel(y[:8], gold["received"]) < RTOL
     assert rel_err(pred[:4, :, :64], gold["logits_slice"]) < RTOL
+    assert _cases.max_rel(pred[:4, :, :64], gold["logits_slice"]) < RTOL
     assert rel_err(torch.logsumexp(pred, -1), gold["lse"]) < RTOL
     tar_real = inp if kind in ("Transeiver_star", "Transeiver_Star") else inp[:, 1:]
     assert abs(float(loss_function(tar_real, pred)) - float(gold["loss"])) < RTOL * float(gold["loss"])
@@ -86,37 +94,59 @@ def test_forward_and_greedy_against_goldens(dev, kind, channel):
     ids_ref = torch.from_numpy(gold["greedy_ids"])
     n_bad, unexplained = explained_mismatches(kind, channel, ids_c, ids_ref, inp.cpu())
     assert unexplained == 0, f"{unexplained} sentences differ from the oracle beyond a numerical tie"
-    assert n_bad <= 1, f"{n_bad} sentences hit fp32-vs-fp32 ties; expected at most one in this seeded case"
+    assert n_bad <= (3 if prec else 1), f"{n_bad} sentences hit ties; expected at most {3 if prec else 1} in this seeded case"
     counts = BleuScore.counts_from_ids(inp, ids).cpu().numpy()
     same = (ids_c == ids_ref).all(1).numpy()
     assert np.array_equal(counts[same], gold["bleu_counts"][same])
     assert np.array_equal(counts, B.bleu_counts(gold["inp"], ids_c.numpy()))
 
 
-@pytest.mark.parametrize("kind", ["Transeiver_Star", "Transeiver_star", "Transeiver"])
-def test_tensor_core_precision_mode(dev, kind, monkeypatch):
-    """prec=1 (tcgen05, bf16x3 split, fused star-cycle kernels): logits within 1e-3 relative of the oracle, greedy ids
-    identical except where the oracle's own fp64 top-2 margin is a numerical tie."""
-    import deepsc_gan_b200.models.modules as M0
-    from deepsc_gan_b200.models.modules import create_masks
+def _margin_run(dev, name):
+    """Greedy decode of one margin case through the product API -> (ids, counts, fixture)."""
+    from deepsc_gan_b200 import sweep
     from deepsc_gan_b200.utlis.eval import greedy_decode_noattack
-    monkeypatch.setattr(M0, "PREC", 1)
-    gold = np.load(_cases.golden_path(kind, "AWGN"))
-    args, net = build(kind, dev)
-    inp = torch.from_numpy(gold["inp"]).to(dev)
-    z, z_r, p, h_z, h_z_r = _cases.draws()
-    n_std = O.snr_to_noise(_cases.SNR_DB)
-    tar_inp = inp[:, :-1]
-    masks = create_masks(inp, tar_inp)
-    with torch.no_grad():
-        pred, x, y, _ = net(inp, tar_inp, p.to(dev), 3.0, "AWGN", n_std, False, *masks, noise=z.to(dev), h=h_z)
-    assert rel_err(x[:8], gold["symbols"]) < RTOL
-    assert rel_err(pred[:4, :, :64], gold["logits_slice"]) < RTOL
-    assert rel_err(torch.logsumexp(pred, -1), gold["lse"]) < RTOL
-    ids = greedy_decode_noattack(args, inp, net, 0.0, "AWGN", n_std, noise=z.to(dev), h=h_z).cpu()
-    n_bad, unexplained = explained_mismatches(kind, "AWGN", ids, torch.from_numpy(gold["greedy_ids"]), inp.cpu())
-    assert unexplained == 0, f"{unexplained} sentences differ from the oracle beyond a numerical tie"
-    assert n_bad <= 3, f"{n_bad} sentences hit ties"
+    from deepsc_gan_b200.utlis.tools import BleuScore
+    kind, channel, _, snr_db, psr_db, _ = _cases.MARGIN_CASES[name]
+    fx = np.load(_cases.margin_path(name))
+    args, net = build(kind, dev, _cases.margin_params(name))
+    inp = torch.from_numpy(fx["inp"]).to(dev)
+    z = _cases.margin_noise(fx["seeds"]).to(dev)
+    n_std = O.snr_to_noise(snr_db)
+    if psr_db is None:
+        ids = greedy_decode_noattack(args, inp, net, 0.0, channel, n_std, noise=z, h=_cases.draws()[3])
+        counts = BleuScore.counts_from_ids(inp, ids)
+    else:                                               # configs[3]: the generator's perturbation at a fixed PSR
+        runner = sweep.SweepRunner(net, 1, channel="AWGN", attack="generator", psr_db=psr_db)
+        ids, counts = runner.run(inp, torch.full((1,), n_std, device=dev), noise=z)
+    return ids.cpu(), counts.cpu().numpy(), fx
+
+
+@pytest.mark.parametrize("name", list(_cases.MARGIN_CASES))
+def test_strict_bit_exact_ids_on_margin_cases(dev, name):
+    """STRICT: all 64 x 31 greedy ids and all 64 x 10 BLEU counts equal the oracle's, in the default arithmetic (prec 1),
+    for every system and every BASELINE.json eval config (baseline AWGN, star AWGN at 0 / 6 / 12 / 18 dB, star Rayleigh,
+    4-layer star, generator attack at fixed PSR), on the seeded Keras initialisation and on the "lively" weight variant
+    whose decoded ids depend on the input.  The cases hold only sentences whose fp64 top-2 logit margin is >= 2e-3 of the
+    logit scale at every step (tests/test_margin_cases.py re-derives that on the CPU), so no tie can excuse a difference."""
+    import deepsc_gan_b200.models.modules as M0
+    assert M0.PREC == 1
+    ids, counts, fx = _margin_run(dev, name)
+    assert ids.dtype == torch.int32 and torch.equal(ids, torch.from_numpy(fx["ids"]))
+    assert np.array_equal(counts, fx["counts"])
+
+
+def test_strict_bit_exact_ids_two_units_two_snrs_one_launch(dev):
+    """The two star AWGN margin cases (6 dB and 0 dB) stacked as two units of one launch: per-unit noise std and power
+    normalisation, ids equal to the per-unit oracle runs."""
+    from deepsc_gan_b200 import engine
+    names = ("Transeiver_Star_AWGN", "Transeiver_Star_AWGN_0dB")
+    fxs = [np.load(_cases.margin_path(n)) for n in names]
+    args, net = build("Transeiver_Star", dev)
+    inp = torch.cat([torch.from_numpy(f["inp"]) for f in fxs]).to(dev)
+    z = torch.cat([_cases.margin_noise(f["seeds"]) for f in fxs]).to(dev)
+    n_std = torch.tensor([O.snr_to_noise(_cases.MARGIN_CASES[n][3]) for n in names], dtype=torch.float32, device=dev)
+    ids = engine.greedy_units(net, inp, 2, n_std, noise=z).cpu()
+    assert torch.equal(ids, torch.cat([torch.from_numpy(f["ids"]) for f in fxs]))
 
 
 def test_multi_unit_greedy_equals_per_unit_oracle(dev):

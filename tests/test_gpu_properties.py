@@ -28,13 +28,6 @@ def build(kind, dev, prec=1):
     return args, net
 
 
-@pytest.fixture(autouse=True)
-def _restore_precision():
-    import deepsc_gan_b200.models.modules as Mod
-    yield
-    Mod.set_precision(0)
-
-
 def test_full_size_sweep_equals_unit_by_unit_and_oracle_sample(dev):
     from deepsc_gan_b200 import engine, sweep
     from deepsc_gan_b200.dataset.synthetic import synthetic_units
@@ -59,12 +52,27 @@ def test_full_size_sweep_equals_unit_by_unit_and_oracle_sample(dev):
     # BLEU counts: the device table equals the host restatement on every sentence of the super-batch
     counts = sweep._lib.bleu_counts(inp.to(dev), ids)
     assert np.array_equal(counts.cpu().numpy(), B.bleu_counts(inp.numpy(), ids.cpu().numpy()))
-    # and two units against the oracle, bit for bit (>= 63 of 64 sentences: a numerical tie may flip one)
+    # and eight of the 37 units against the oracle: every sentence equal, except where the first differing step is a
+    # numerical tie in the oracle's own fp64 logits (random sentences; the strict no-excuse comparison is
+    # test_gpu_models.py::test_strict_bit_exact_ids_on_margin_cases)
     P = _cases.params(kind)
-    for u in (5, 30):
+    P64 = O.to_dtype(P, torch.float64)
+    n_diff = 0
+    for u in (0, 5, 9, 14, 19, 24, 30, 36):
         sl = slice(64 * u, 64 * u + 64)
         ref = O.greedy_decode_noattack(P, O.Spec(kind), inp[sl].long(), 0.0, "AWGN", float(n_std[u]), z[sl])
-        assert (ids[sl].cpu() == ref).all(1).float().mean() >= 63 / 64, u
+        got = ids[sl].cpu()
+        bad = (got != ref).any(1).nonzero()[:, 0].tolist()
+        n_diff += len(bad)
+        if bad:
+            _, lg = O.greedy_decode_noattack(P64, O.Spec(kind), inp[sl].long(), 0.0, "AWGN", float(n_std[u]), z[sl].double(),
+                                             return_logits=True)
+            for b in bad:
+                t = int((got[b] != ref[b]).nonzero()[0]) - 1
+                row = lg[b, t]
+                gap = abs(float(row[int(got[b, t + 1])] - row[int(ref[b, t + 1])]))
+                assert gap <= 1e-4 * float(row.abs().max()), (u, b, t, gap)
+    assert n_diff <= 8, n_diff
 
 
 def test_ragged_unit_counts_and_extreme_sentences(dev):

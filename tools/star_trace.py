@@ -1,4 +1,5 @@
-"""Timeline of one tile of the fused star kernel (CTA 0): where a cycle's ~15 us go.  Debug tool, not a benchmark.
+"""Timeline of one tile of the fused star kernel (CTA 0): where a cycle's ~12 us go.  Debug tool, not a benchmark.
+Needs the debug-tools library (`python deepsc-gan_b200/build.py --debug`: the product sources with -DDSC_DEBUG_TOOLS=1).
 
     python tools/star_trace.py [prec] [n2] [cycles]
 """
@@ -11,6 +12,8 @@ import torch
 import deepsc_gan_b200  # noqa: F401
 from deepsc_gan_b200 import _lib as L
 import deepsc_gan_b200.models.modules as M
+
+L.use_debug_library()          # the trace hooks are compiled out of libdeepsc_b200.so
 
 prec = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 n2 = int(sys.argv[2]) if len(sys.argv) > 2 else 17

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import deepsc_gan_b200  # noqa
 from deepsc_gan_b200 import _lib as L
+L.use_debug_library()      # python deepsc-gan_b200/build.py --debug
 lib = L.load()
 out = torch.zeros(1, dtype=torch.int64, device="cuda:0")
 iters = 2000
