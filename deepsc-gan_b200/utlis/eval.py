@@ -26,6 +26,11 @@ from ..models.modules import create_look_ahead_mask, create_masks, create_paddin
 from .tools import BleuScore, SeqtoText, SNR_to_noise
 
 
+# Arithmetic of the taped pass that yields the FGM direction (see models.modules.precision): fp32.  Every other forward of
+# the evaluators (the attacked pass, the bisection forwards, the greedy loops) runs in the package default (tcgen05 bf16x3).
+GRADIENT_PREC = 0
+
+
 @contextlib.contextmanager
 def _frozen(net):
     """The evaluators differentiate with respect to the channel symbols only: parameters do not require grad."""
@@ -65,7 +70,7 @@ def _symbol_gradient(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks,
     channel the eval_step_* functions take the direction from a second, AWGN forward (utlis/eval.py:204-211); the greedy
     decoders differentiate the forward of the given channel itself (:25-33, :137-144).
     Returns (loss, predictions, gradient, outs)."""
-    with _frozen(net), differentiable():
+    with _frozen(net), differentiable(), M.precision(GRADIENT_PREC):
         kw = dict(noise_r=noise, h_r=h, traingan=False) if gan else dict(noise=noise, h=h)
         outs = _call(net, inp, tar_inp, None, PNR_dB, channel, n_std, masks, **kw)
         pred = outs[1] if gan else outs[0]
@@ -174,7 +179,7 @@ def eval_step_normal_pgd(inp, tar, net, PNR_dB, channel='AWGN', n_std=0.1, epsil
 
 def _pgd_first(net, inp, tar_inp, tar_real, PNR_dB, channel, n_std, masks, noise, h):
     """First pass of eval_step_normal_pgd: the gradient is w.r.t. the received symbols y of the given channel (:250)."""
-    with _frozen(net), differentiable():
+    with _frozen(net), differentiable(), M.precision(GRADIENT_PREC):
         outs = _call(net, inp, tar_inp, None, PNR_dB, channel, n_std, masks, noise=noise, h=h)
         loss = loss_function(tar_real, outs[0])
         (g,) = torch.autograd.grad(loss, outs[3])

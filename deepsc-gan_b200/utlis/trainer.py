@@ -11,8 +11,8 @@ import torch
 
 from .. import _lib
 from .. import optim as O
-from ..models.modules import create_masks, differentiable, loss_function
-from .eval import fgm_perturbation
+from ..models.modules import create_masks, differentiable, loss_function, precision
+from .eval import GRADIENT_PREC, fgm_perturbation
 
 
 def make_optimizer(net, learning_rate: float = 5e-4, n_grad_buffers: int = 2, **adam_kw) -> O.Adam:
@@ -54,7 +54,7 @@ def train_attack_step(inp, tar, p, PNR_dB, net, optim_net, channel='AWGN', n_std
     tar_inp, tar_real = tar[:, :-1], tar
     masks = create_masks(inp, tar_inp)
     fp = optim_net.fp
-    with differentiable():
+    with differentiable(), precision(GRADIENT_PREC):       # the FGM direction is taken in fp32 (utlis/eval.py GRADIENT_PREC)
         outs = _forward(net, inp, tar_inp, p, PNR_dB, channel, n_std, masks, noise=noise, h=h)
         loss = loss_function(tar_real, outs[0])
         (g,) = torch.autograd.grad(loss, outs[3])

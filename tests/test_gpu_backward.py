@@ -311,10 +311,14 @@ def oracle_param_grads(kind, inp, z, z_r=None, p=None, PNR_dB=3.0, traingan=Fals
     return P, loss, None
 
 
+@pytest.mark.parametrize("prec,gtol", [(1, 5e-3), (0, GTOL)])
 @pytest.mark.parametrize("kind", ["Transeiver_Star", "Transeiver", "Transeiver_star"])
-def test_parameter_gradients_match_oracle_autograd(dev, kind):
-    """d CE / d(every parameter) of a teacher-forced AWGN forward with a perturbation, whole model."""
+def test_parameter_gradients_match_oracle_autograd(dev, kind, prec, gtol):
+    """d CE / d(every parameter) of a teacher-forced AWGN forward with a perturbation, whole model: in the default
+    arithmetic (prec 1; a bf16x3 product carries ~2^-17 relative error, ten times fp32's, and the star recurrences
+    amplify it: 5e-3 of the gradient's L2 norm) and with fp32 products (prec 0: 1e-3)."""
     import deepsc_gan_b200.models.modules as Mod
+    Mod.set_precision(prec)
     args, net = build(kind, dev)
     inp = _cases.synthetic_unit(1)
     z, _, p, _, _ = _cases.draws()
@@ -338,8 +342,8 @@ def test_parameter_gradients_match_oracle_autograd(dev, kind):
         worst_max.append((rel_err(prm.grad, ref), name))
     worst.sort(reverse=True)
     worst_max.sort(reverse=True)
-    assert worst[0][0] < GTOL, worst[:5]
-    assert worst_max[0][0] < 1e-2, worst_max[:5]
+    assert worst[0][0] < gtol, worst[:5]
+    assert worst_max[0][0] < 10 * gtol, worst_max[:5]
 
 
 def test_fgm_eval_steps_match_oracle(dev):
@@ -370,16 +374,20 @@ def test_fgm_eval_steps_match_oracle(dev):
 def test_fgm_attacked_greedy_decoders_match_oracle(dev):
     """greedy_decode (utlis/eval.py:11-75) on a star and on the baseline system and greedy_decode_gan (:120-187): the
     scaled FGM perturbation (hence d loss / d received symbols), the symbols, the realised noise, the teacher-forced
-    clean-branch argmax ``noa`` and the greedy ids against the oracle's restatement of the same functions."""
+    clean-branch argmax ``noa`` and the greedy ids against the oracle's restatement of the same functions.  The oracle
+    runs in fp64 here: the per-sample normalisation of the direction is ill-conditioned for a sentence whose gradient is
+    small, and the fp32 oracle itself is 1.7e-2 away from the fp64 one on the Rayleigh case below."""
     from deepsc_gan_b200.utlis import eval as E
     z, z2, _, h_z, _ = _cases.draws()
     n_std = O.snr_to_noise(_cases.SNR_DB)
     inp = _cases.synthetic_unit(3)
+    P64 = lambda kind: O.to_dtype(_cases.params(kind), torch.float64)
     for kind in ("Transeiver_Star", "Transeiver"):
         args, net = build(kind, dev)
         outputs, scaled, noise, x = E.greedy_decode(args, inp.to(dev), net, 6.0, channel="AWGN", n_std=n_std, epsilon=1,
                                                     noise=z.to(dev), noise2=z2.to(dev))
-        ref_ids, ref_scaled, ref_x = O.greedy_decode(_cases.params(kind), O.Spec(kind), inp.long(), 6.0, "AWGN", n_std, z, z2)
+        ref_ids, ref_scaled, ref_x = O.greedy_decode(P64(kind), O.Spec(kind), inp.long(), 6.0, "AWGN", n_std, z.double(),
+                                                     z2.double())
         assert tuple(outputs.shape) == (64, 31) and outputs.dtype == torch.int32
         assert rel_err(x, ref_x) < 1e-3 and rel_err(noise, n_std * z2) < 1e-3
         assert rel_err(scaled, ref_scaled) < 2e-3, kind
@@ -388,15 +396,15 @@ def test_fgm_attacked_greedy_decoders_match_oracle(dev):
     args, net = build("Transeiver_Star", dev)
     outputs, scaled, noise, x = E.greedy_decode(args, inp.to(dev), net, 6.0, channel="Rayleigh", n_std=n_std, noise=z.to(dev),
                                                 noise2=z2.to(dev), h=h_z)
-    ref_ids, ref_scaled, _ = O.greedy_decode(_cases.params("Transeiver_Star"), O.Spec("Transeiver_Star"), inp.long(), 6.0,
-                                             "Rayleigh", n_std, z, z2, h_z)
+    ref_ids, ref_scaled, _ = O.greedy_decode(P64("Transeiver_Star"), O.Spec("Transeiver_Star"), inp.long(), 6.0, "Rayleigh",
+                                             n_std, z.double(), z2.double(), h_z)
     assert noise is None and rel_err(scaled, ref_scaled) < 2e-3
     assert (outputs.cpu() == ref_ids).all(1).float().mean() >= 62 / 64
     # GAN model
     args, gan = build("Transeiver_GAN", dev)
-    P, spec = _cases.params("Transeiver_GAN"), O.Spec("Transeiver_GAN")
+    spec = O.Spec("Transeiver_GAN")
     out = E.greedy_decode_gan(args, inp.to(dev), gan, 6.0, channel="AWGN", n_std=n_std, noise=z.to(dev), noise2=z2.to(dev))
-    ref = O.greedy_decode_gan(P, spec, inp.long(), 6.0, "AWGN", n_std, z, z2)
+    ref = O.greedy_decode_gan(P64("Transeiver_GAN"), spec, inp.long(), 6.0, "AWGN", n_std, z.double(), z2.double())
     assert len(out) == 5 and tuple(out[0].shape) == (64, 31) and tuple(out[1].shape) == (64, 30)
     assert (out[0].cpu() == ref[0]).all(1).float().mean() >= 62 / 64
     assert (out[1].cpu() == ref[1]).float().mean() > 0.995                  # noa: teacher-forced argmax of the clean branch
@@ -611,8 +619,9 @@ def test_gan_train_step_literal_layer_names_also_update_the_channel_encoder(dev)
                           noise=z.to(dev), noise_r=z_r.to(dev), p_draw=p_draw.to(dev), step_c_literal_names=literal)
         res[literal] = {n: p.detach().clone() for n, p in gan.named_parameters()}
     for n in res[False]:
-        same = torch.equal(res[False][n], res[True][n])
-        assert same != n.startswith("channel_encoder."), n
+        # (two runs differ in isolated elements anyway: atomics in the embedding / split-K accumulations)
+        moved = ((res[False][n] - res[True][n]).abs() > 1e-4).float().mean().item()
+        assert (moved > 0.5) if n.startswith("channel_encoder.") else (moved < 0.01), (n, moved)
 
 
 def test_training_with_dropout_runs(dev):

@@ -283,14 +283,14 @@ def test_vocab_argmax_and_ce_rows(L, dev):
     wd = torch.zeros(128, (V + 127) // 128 * 128, device=dev)
     wd[:, :V] = w.to(dev)
     ids = torch.zeros(96, 3, dtype=torch.int32, device=dev)
-    L.vocab_argmax(x.to(dev), wd, b.to(dev), V, ids[:, 1])
+    L.vocab_argmax(x.to(dev), wd, b.to(dev), V, ids[:, 1], prec=0)
     top2 = logits.topk(2, -1).values
     clear = (top2[:, 0] - top2[:, 1]) > 1e-5          # rows whose fp64 margin is not a numerical tie
     assert clear.float().mean() > 0.95
     assert torch.equal(ids[:, 1].cpu()[clear].long(), logits.argmax(-1)[clear])
     assert bool((ids[:, 0] == 0).all()) and bool((ids[:, 2] == 0).all())
     lg = torch.empty(96, V, device=dev)
-    L.vocab_argmax(x.to(dev), wd, b.to(dev), V, ids[:, 2], logits=lg)
+    L.vocab_argmax(x.to(dev), wd, b.to(dev), V, ids[:, 2], logits=lg, prec=0)
     assert rel_err(lg, logits) < 2e-6
     tgt = torch.randint(0, V, (96,), generator=g)
     tgt[::5] = 0
@@ -411,7 +411,7 @@ def test_linear_tensor_core_row_skip_strided(L, dev):
     assert rel_err(tile[:, 31, :], ref[:4]) < 3e-5 and float(tile[:, :31].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("prec,tol", [(1, 1e-4), (2, 5e-2)])
+@pytest.mark.parametrize("prec,tol", [(1, 2e-4), (2, 1e-1)])
 @pytest.mark.parametrize("S,n2", [(4, 0), (600, 17), (2368, 30)])
 def test_star_cycles_at_bench_sizes_match_literal_oracle(L, dev, S, n2, prec, tol, monkeypatch):
     """dsc_star_cycles_tc at one tile, at a size that does not fill the SMs evenly and at bench.py's 592 tiles (4 per SM):
