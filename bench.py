@@ -39,7 +39,9 @@ UNIT = "sentences/s"
 SNRS = list(range(19))
 # dram__bytes_read.sum + dram__bytes_write.sum of one star_fused_kernel<3> launch (8 cycles) from the `ncu --set full`
 # capture summarised in profiles/ (keyed by sentences per launch); null when no capture exists for the size that ran
-ROOFLINE_TRAFFIC_BYTES = {2368: 200217600 + 28533504}   # profiles/r01_ncu_star_fused.txt (full 8-cycle launch, n2 = 17)
+ROOFLINE_TRAFFIC_BYTES = {2368: 200262912 + 27648512}   # profiles/r02_ncu_star_fused.txt (full 8-cycle launch, n2 = 17)
+# sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the same capture (the kernel at its own clock)
+NCU_TENSOR_ACTIVE_PCT = {2368: 38.8}
 
 
 def load_peaks():
@@ -84,8 +86,11 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-def cpu_oracle_rate(n_units: int, first_unit: int = 0):
-    """Oracle greedy decode + BLEU counts over ``n_units`` units (one SNR point each, cycling the sweep)."""
+def cpu_oracle_rate(n_units: int, first_unit: int = 0, last_only: bool = True):
+    """Oracle greedy decode + BLEU counts over ``n_units`` units (one SNR point each, cycling the sweep).
+    ``last_only=False`` is greedy as the reference writes it (utlis/eval.py:106-113: the decoder's vocabulary projection
+    over the whole prefix at every step); ``True`` projects the newest position only (same ids, the reference's CPU path
+    given the one optimisation any port would make)."""
     from deepsc_gan_b200.dataset.synthetic import synthetic_unit
     from oracle import bleu_oracle, deepsc_oracle as O
     torch.set_num_threads(os.cpu_count())
@@ -97,7 +102,7 @@ def cpu_oracle_rate(n_units: int, first_unit: int = 0):
             inp = synthetic_unit(first_unit + u).long()
             g = torch.Generator().manual_seed(7 + u)
             z = torch.randn(64, 31, 16, generator=g)
-            ids = O.greedy_decode_noattack(P, spec, inp, 0.0, "AWGN", O.snr_to_noise(SNRS[u % 19]), z)
+            ids = O.greedy_decode_noattack(P, spec, inp, 0.0, "AWGN", O.snr_to_noise(SNRS[u % 19]), z, last_only=last_only)
             bleu_oracle.bleu_counts(inp.numpy(), ids.numpy())
     dt = time.perf_counter() - t0
     return 64 * n_units / dt, dt
@@ -135,6 +140,53 @@ def workload_config(units: int, world: int):
             "l2_policy": "per-step working set (activations + logits workspace) exceeds the 126 MB L2"}
 
 
+def train_leg(cfg, dev, rank, world, bs, steps, barrier):
+    """BASELINE.json configs[4]: one ``gan_train_step`` (Transeiver_GAN forward, two backward sweeps, three Adam
+    applications; utlis/gan_train.py:8-50) per step on ``bs`` sentences per rank, CUDA-graph replayed; under torchrun
+    the flat gradient bucket is all-reduced over NCCL once per step.  Device-timed, max over ranks."""
+    import torch.distributed as dist
+    from deepsc_gan_b200 import models, sweep
+    from deepsc_gan_b200.dataset.synthetic import synthetic_units
+    from deepsc_gan_b200.models import modules
+    from deepsc_gan_b200.utlis import gan_train as GT
+    modules.set_precision(1)
+    torch.manual_seed(2024)                                        # identical initial weights on every rank
+    net = models.Transeiver_GAN(cfg).to(dev).train()
+    opt = GT.make_optimizer(net, learning_rate=cfg.lr)
+    torch.manual_seed(100 + rank)                                  # per-rank noise and dropout
+    modules.set_dropout_seed(7000 + rank)
+    n_u = (bs + 63) // 64
+    batches = [synthetic_units((rank * 64 + s) * n_u, n_u)[:bs].to(dev) for s in range(4)]
+    step = GT.GraphedGanTrainStep(net, opt, 0.5, n_std=float(sweep.snr_to_noise(3.0)), traingan=True)
+    for s in range(3):
+        out = step(batches[s % 4])
+    first = float(out[0])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        out = step(batches[s % 4])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    digest = opt.fp.flat.double().sum().reshape(1)
+    same = True
+    if world > 1:
+        parts = [torch.empty_like(digest) for _ in range(world)]
+        dist.all_gather(parts, digest)
+        same = all(bool(torch.equal(q, parts[0])) for q in parts)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    res = {"workload": "Transeiver_GAN gan_train_step (forward + 2 backward sweeps + 3 Adam applies), AWGN 3 dB, graph-replayed",
+           "batch_per_rank": bs, "n_gpus": world, "steps": steps, "ms_per_step": ms,
+           "sentences_per_s": bs * world / (ms * 1e-3), "all_reduce_bytes_per_step": int(opt.fp.grad_bucket.numel()) * 4 if world > 1 else 0,
+           "replicas_identical": same, "loss_first": first, "loss_last": float(out[0])}
+    del step, net, opt
+    torch.cuda.synchronize()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -146,6 +198,8 @@ def main():
     ap.add_argument("--cpu-units", type=int, default=32, help="units of the cpu_baseline sample (N=1 only): ~15 s of CPU work")
     ap.add_argument("--prec", type=int, default=1, help="0 fp32 FFMA, 1 tcgen05 bf16x3, 2 tcgen05 bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=20, help="timed steps of the config-5 training leg (0 = skip)")
+    ap.add_argument("--train-bs-large", type=int, default=512, help="second training figure at this batch per rank (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -266,6 +320,8 @@ def main():
                 "peak_source": f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json bf16_tflops_sustained)",
                 "launches_timed": len(dom), "mean_launch_ms": mean_ms, "algorithmic_flops_per_launch": flops,
                 "tensor_passes_per_flop": passes, "algorithmic_tflops": flops / (mean_ms * 1e-3) / 1e12,
+                "frac_algorithmic": flops / (mean_ms * 1e-3) / 1e12 / peak,
+                "tensor_active_pct": NCU_TENSOR_ACTIVE_PCT.get(S),
                 "share_of_step": sum(t for t, _ in dom) / t_ms,
                 "arith": {1: "bf16x3 tcgen05 (3 bf16 UMMA passes per fp32-class product), fp32 accumulate/softmax",
                           2: "bf16 tcgen05"}[args.prec]}
@@ -282,6 +338,19 @@ def main():
                     "traffic": None, "peak_source": f"{peaks['source']} HBM copy bandwidth", "launches_timed": len(dom),
                     "mean_launch_ms": mean_ms, "bytes_per_launch": nbytes, "share_of_step": sum(t for t, _ in dom) / t_ms}
 
+    # ---- config 5: the data-parallel GAN training step on the same ranks -----------------------------------
+    train = None
+    if args.train_steps > 0:
+        train = {}
+        for key, bs in (("bs64", 64), ("bs_large", args.train_bs_large)):
+            if bs <= 0:
+                continue
+            try:
+                train[key] = train_leg(cfg, dev, rank, world, bs, args.train_steps, barrier)
+            except Exception as e:                                   # the eval line must survive a training failure
+                train[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        modules.set_precision(args.prec)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -295,11 +364,18 @@ def main():
             "e2e": {"value": sentences / (t_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": S * 31 * 4,
                     "d2h_bytes_per_step": S * 10 * 4},
             "roofline": roof}
+    if train is not None:
+        line["train"] = train
     if world == 1 and not args.no_cpu_baseline:
         rate, dt = cpu_oracle_rate(args.cpu_units)
+        n_aw = max(1, args.cpu_units // 4)
+        rate_aw, dt_aw = cpu_oracle_rate(n_aw, last_only=False)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{args.cpu_units} units ({64 * args.cpu_units} sentences) of the same workload, oracle greedy "
-                                          f"(last-position logits), {dt:.1f} s wall"}
+                                          f"(last-position logits), {dt:.1f} s wall",
+                                "as_written": {"value": rate_aw, "unit": UNIT, "cores": os.cpu_count(),
+                                               "sample": f"{n_aw} units ({64 * n_aw} sentences), greedy as utlis/eval.py:106-113 writes it "
+                                                         f"(vocabulary logits of the whole prefix every step), {dt_aw:.1f} s wall"}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -89,6 +89,14 @@ class Adam:
                          None if grad2 is None else grad2[b:e], grad2_scale)
 
 
+def mean_scale(group=None) -> float:
+    """1/world inside a process group, else 1: the factor Adam folds into its gradient read after a SUM all-reduce."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    return 1.0 / dist.get_world_size(group)
+
+
 def all_reduce_mean_scale(bucket: torch.Tensor, group=None) -> float:
     """Sum the flat gradient bucket over the data-parallel ranks (NCCL) and return the 1/world factor that the Adam
     kernel folds into its gradient read.  No-op (factor 1) outside a process group."""
