@@ -4,7 +4,8 @@
 adds the id-domain path the eval loop uses on the GPU: ``counts_from_ids`` runs the integer n-gram
 kernel (dsc_bleu_counts) and ``score_from_counts`` forms the float score on the host in fp64 with the
 formula of nltk's ``sentence_bleu`` (method0 smoothing), see SURVEY.md App. D.  ``Similarity`` (BERT
-cosine, tools.py:53-103) needs bert4keras and a BERT checkpoint that the reference does not ship; out of scope.
+cosine, tools.py:53-103) keeps the reference's scoring arithmetic (``similarity_from_features``); the BERT encoder it
+scores (bert4keras + a checkpoint the reference does not ship) is injected by the caller.
 """
 from __future__ import annotations
 
@@ -108,3 +109,43 @@ def SNR_to_noise(snr):
     snr = 10 ** (snr / 10)
     noise_std = 1 / np.sqrt(snr)
     return noise_std
+
+
+def similarity_from_features(vector1, vector2) -> List[float]:
+    """The arithmetic of ``Similarity.compute_score`` after the two BERT forwards (utlis/tools.py:84-103):
+    features [n, positions, hidden] are summed over positions, each feature COLUMN is divided by its maximum absolute
+    value over the batch (sklearn ``normalize(axis=0, norm='max')``: the score of a sentence depends on the batch it is
+    scored in), and the row-wise cosine is returned."""
+    v1 = np.asarray(vector1, dtype=np.float64).sum(axis=1)
+    v2 = np.asarray(vector2, dtype=np.float64).sum(axis=1)
+
+    def _max_norm_columns(v):
+        m = np.abs(v).max(axis=0)
+        m[m == 0.0] = 1.0                                          # sklearn leaves all-zero columns untouched
+        return v / m
+
+    v1, v2 = _max_norm_columns(v1), _max_norm_columns(v2)
+    dot = np.einsum("ij,ij->i", v1, v2)
+    return (dot / (np.sqrt(np.einsum("ij,ij->i", v1, v1)) * np.sqrt(np.einsum("ij,ij->i", v2, v2)))).tolist()
+
+
+class Similarity:
+    """utlis/tools.py:53-103.  The reference builds a bert4keras model from (config_path, checkpoint_path, dict_path) and
+    takes the output of layer 'Encoder-11-FeedForward-Norm'; neither bert4keras nor a checkpoint exists in this image or in
+    the reference tree, so the encoder is a callable the caller supplies:
+
+        encoder(list_of_sentences) -> float array [n, 32, hidden]    (tokenise, pad to 32 post, run BERT)
+
+    ``compute_score`` then follows the reference: tags removed from both sentences, both batches encoded, scored with
+    ``similarity_from_features``.  Without an encoder the constructor raises - there is no silent substitute metric."""
+
+    def __init__(self, config_path=None, checkpoint_path=None, dict_path=None, *, encoder=None):
+        if encoder is None:
+            raise RuntimeError("Similarity needs a BERT sentence encoder (bert4keras + checkpoint are not available): "
+                               "pass encoder=callable(sentences) -> [n, 32, hidden] features")
+        self.config_path, self.checkpoint_path, self.dict_path, self.encoder = config_path, checkpoint_path, dict_path, encoder
+
+    def compute_score(self, real: Sequence[str], predicted: Sequence[str]) -> List[float]:
+        real = [_RE_TAGS.sub('', s) for s in real]
+        predicted = [_RE_TAGS.sub('', s) for s in predicted]
+        return similarity_from_features(self.encoder(real), self.encoder(predicted))

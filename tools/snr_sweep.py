@@ -53,7 +53,14 @@ def main():
     net = getattr(models, a.system)(cfg).to(dev).eval()
     if a.weights:
         net.load_tf_state_dict(torch.load(a.weights, map_location=dev))
-    units = dataloader.return_dataset(cfg, a.data, -1, shuffle=False).as_units() if a.data else synthetic_units(0, a.units)
+    if a.data and a.data.endswith(".npz"):
+        # tests/golden/europarl_test.npz: the reference's test_data.pkl already padded (make_europarl_fixture.py); the
+        # [:-1] slice and the full-unit cut are dataset/dataloader.py:11-14's
+        import numpy as np
+        ids = torch.from_numpy(np.load(a.data)["ids"].astype(np.int32))[:-1]
+        units = ids[: ids.shape[0] // 64 * 64]
+    else:
+        units = dataloader.return_dataset(cfg, a.data, -1, shuffle=False).as_units() if a.data else synthetic_units(0, a.units)
     K = 1 if a.channel == "Rician" else 0
     runner = sweep.SweepRunner(net, a.units_per_launch, channel="AWGN" if a.channel == "AWGN" else "Rayleigh", detector=a.detector,
                                seed=1, attack=a.attack, psr_db=a.psr_db)
@@ -68,6 +75,8 @@ def main():
             pickle.dump(rows, f)
         with open(os.path.splitext(a.out)[0] + "-counts.pkl", "wb") as f:
             pickle.dump({"counts": counts.numpy(), "snr_index": snr_index}, f)
+        with open(os.path.splitext(a.out)[0] + "-rows.json", "w") as f:
+            json.dump([[float(v) for v in r] for r in rows], f)
         n_eval = len(snr_index)
         print(json.dumps({"system": a.system, "channel": a.channel, "sentences": int(units.shape[0]), "snr_points": len(rows),
                           "sentence_evaluations": n_eval, "n_gpus": world, "seconds": t0.elapsed_time(t1) * 1e-3,
