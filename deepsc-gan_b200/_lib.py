@@ -86,8 +86,10 @@ def use_debug_library() -> None:
 
 def load() -> C.CDLL:
     """Load the shared library (no GPU needed for this step) and set the prototypes."""
-    global _lib
+    global _lib, LIB_PATH
     if _lib is None:
+        if os.environ.get("DSC_LIB_PATH"):              # developer A/B builds (tools/pp_variants.sh); never set in product use
+            LIB_PATH = os.environ["DSC_LIB_PATH"]
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
@@ -112,6 +114,9 @@ STATS = {"launches": 0}
 PROFILE = None
 STAR_FIRST_SAT_DONE = 0x100          # include/deepsc_b200.h DSC_STAR_FIRST_SAT_DONE
 STAR_NO_FINAL_RELAY = 0x200          # include/deepsc_b200.h DSC_STAR_NO_FINAL_RELAY
+STAR_FORM_ONE_TILE = 0x400           # include/deepsc_b200.h DSC_STAR_FORM_ONE_TILE / _TWO_TILE: force a kernel form
+STAR_FORM_TWO_TILE = 0x800
+STAR_FORM = 0                        # OR-ed into every dsc_star_cycles_tc call (0 = let the library pick by batch size)
 PROFILE_OPS = ("dsc_star_cycles_tc",)
 
 
@@ -324,7 +329,8 @@ def star_cycles_tc(xi0: torch.Tensor, s0: torch.Tensor, q0: torch.Tensor, kvei: 
                                          packed_weight(w_grouped, 384).data_ptr(), packed_weight(wo, 128).data_ptr(),
                                          packed_weight(wkv_relay, 256).data_ptr(), packed_weight(wo_relay, 128).data_ptr(),
                                          packed_weight(wq_relay, 128).data_ptr(), bias_o.data_ptr(),
-                                         bias_o_relay.data_ptr(), x_rowmajor.data_ptr(), n_sent, n_cycles, prec, _stream()),
+                                         bias_o_relay.data_ptr(), x_rowmajor.data_ptr(), n_sent, n_cycles, prec | STAR_FORM,
+                                         _stream()),
                "dsc_star_cycles_tc")
     return x_rowmajor
 

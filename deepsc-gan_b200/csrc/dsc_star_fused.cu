@@ -61,8 +61,6 @@ using namespace tc;
 
 namespace sf {
 constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = 576;
-constexpr int STAGES = 2;                                     // 3 stages: 5 % slower (213 KB of shared memory leave too little L1 for the key streams and spill slots)
-constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
 constexpr uint32_t ACC_Q = ACC1 + 96;                         // J8's 16 columns: behind the 96 columns of a QKV job
 // Issue order of a cycle: J0..J3, then J8 (the query q' of THIS cycle's relay attention, from the previous cycle's s';
@@ -87,9 +85,6 @@ struct Seq {
     return i;
   }
 };
-constexpr uint32_t RB_PLANE = 16 * 128;                       // relay-vector operand: one (part, kb) plane = 16 rows x 128 B
-constexpr uint32_t RB_BYTES = 4 * RB_PLANE;                   // 8 KB behind the ring
-
 struct Bars {
   uint64_t w_full[STAGES], w_free[STAGES];
   uint64_t acc_full[2], acc_free[2];
@@ -97,57 +92,7 @@ struct Bars {
   uint64_t ta_ready;                        // the first half of ATT (heads 0..3 = K-block 0 of J4's operand) is staged
   uint64_t q_full;                          // the relay query q' (J8) is in its accumulator columns
 };
-struct Weights {
-  const uint8_t* qkv;    // grouped [Wq|Wk|Wv]_sat, 384 rows
-  const uint8_t* wo;     // Wo_sat, 128 rows
-  const uint8_t* wkv;    // [Wk|Wv]_relay, 256 rows
-  const uint8_t* wo_r;   // Wo_relay
-  const uint8_t* wq_r;   // Wq_relay
-};
-// chunk j of a cycle: source blob, rows per plane, first row, rows of the blob (n_pad)
-__device__ __forceinline__ void chunk_of(const Weights& w, int j, const uint8_t*& blob, uint32_t& rows, uint32_t& row0, uint32_t& n_pad) {
-  if (j < 4)       { blob = w.qkv;  rows = 96;  row0 = 96u * j; n_pad = 384; }
-  else if (j == 4) { blob = w.wo;   rows = 128; row0 = 0;       n_pad = 128; }
-  else if (j == 5) { blob = w.wkv;  rows = 128; row0 = 0;       n_pad = 256; }
-  else if (j == 6) { blob = w.wkv;  rows = 128; row0 = 128;     n_pad = 256; }
-  else if (j == 7) { blob = w.wo_r; rows = 128; row0 = 0;       n_pad = 128; }
-  else             { blob = w.wq_r; rows = 128; row0 = 0;       n_pad = 128; }
-}
 }  // namespace sf
-
-// 64 fp32 values in shared memory -> 32 hi + 32 lo packed bf16 words (plain loads: load_half_row uses ld.global.nc)
-__device__ __forceinline__ void split_half_row_smem(const float* p, uint32_t* hi, uint32_t* lo) {
-#pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const float4 v = reinterpret_cast<const float4*>(p)[q];
-    split2(v.x, v.y, hi[2 * q], lo[2 * q]);
-    split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
-  }
-}
-
-// 32 fp32 values -> 16 hi + 16 lo packed bf16 words; src = element (k4 = 0, this row), consecutive k4 `stride4` float4 apart
-__device__ __forceinline__ void load_quarter_row(const float4* __restrict__ src, int stride4, uint32_t* hi, uint32_t* lo) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 v = __ldg(src + (int64_t)q * stride4);
-    split2(v.x, v.y, hi[2 * q], lo[2 * q]);
-    split2(v.z, v.w, hi[2 * q + 1], lo[2 * q + 1]);
-  }
-}
-__device__ __forceinline__ void split_quarter_row(const float* v, uint32_t* hi, uint32_t* lo) {
-#pragma unroll
-  for (int q2 = 0; q2 < 16; ++q2) split2(v[2 * q2], v[2 * q2 + 1], hi[q2], lo[q2]);
-}
-// operand columns of k = 32*sub .. 32*sub+31: 16 hi columns and 16 lo columns
-template <int NPASS>
-__device__ __forceinline__ void store_quarter_row(uint32_t lane_addr, uint32_t a_hi, uint32_t a_lo, int sub,
-                                                  const uint32_t* hi, const uint32_t* lo) {
-  tmem_st16(lane_addr + a_hi + sub * 16, hi);
-  if (NPASS == 3) tmem_st16(lane_addr + a_lo + sub * 16, lo);
-}
-__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(n) : "memory");
-}
 
 // Debug timeline (tools/star_trace.py): when a buffer is registered with dsc_debug_star_trace, CTA 0 stamps clock64()
 // at the hand-offs of its first tile: issuer [0, 256) = (operands ready, UMMAs + commits issued) per job; compute warp 0
@@ -158,51 +103,6 @@ __device__ unsigned long long* g_star_trace = nullptr;
 #define g_star_trace ((unsigned long long*)nullptr)
 #endif
 #define DSC_TR(base) do { if (TRACE) { if (tr_buf && tr_n < 256) tr_buf[(base) + tr_n] = (unsigned long long)clock64(); ++tr_n; } } while (0)
-
-// relay GEMVs (J7, J8) in transposed form: D[feature][sentence] = W^T (A, the streamed chunk, M = 128) x vectors (B, N = 16
-// rows of which 4 are sentences).  passes: w_hi*v_hi, w_hi*v_lo, w_lo*v_hi - the same products in the same order as
-// issue_group's hi*hi, lo*hi, hi*lo with the activations as A.
-template <int NPASS>
-__device__ __forceinline__ void issue_relay_gemv(uint32_t d_tmem, uint32_t w_base, uint32_t v_base) {
-  constexpr uint32_t IDESC = idesc_bf16_f32(128, 16);
-#pragma unroll
-  for (int pass = 0; pass < NPASS; ++pass) {
-    const uint32_t pw = (pass == 2) ? 1u : 0u, pv = (pass == 1) ? 1u : 0u;
-#pragma unroll
-    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        umma_ss(d_tmem, smem_desc_sw128(w_base + (pw * 2 + kb) * (128u * 128u) + ks * 32u),
-                smem_desc_sw128(v_base + (pv * 2 + kb) * sf::RB_PLANE + ks * 32u), IDESC, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
-  }
-}
-// one K-block (64 of the 128 k) of a TS-mode job, all passes: J4 starts on the first half of ATT while the satellite
-// attention of heads 4..7 is still running (K-block-major accumulation order for this job)
-template <int NPASS, int N>
-__device__ __forceinline__ void issue_group_kb(uint32_t tmem_base, uint32_t acc_col, uint32_t a_hi, uint32_t a_lo,
-                                               uint32_t b_base, uint32_t b_plane_bytes, int kb, bool first) {
-  constexpr uint32_t IDESC = idesc_bf16_f32(128, N);
-#pragma unroll
-  for (int pass = 0; pass < NPASS; ++pass) {
-    const uint32_t a_col = (pass == 1) ? a_lo : a_hi;               // hi*hi, lo*hi, hi*lo
-    const uint32_t pb = (pass == 2) ? 1u : 0u;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint64_t db = smem_desc_sw128(b_base + (pb * 2 + kb) * b_plane_bytes + ks * 32u);
-      umma_ts(tmem_base + acc_col, tmem_base + a_col + (uint32_t)(kb * 4 + ks) * 8u, db, IDESC,
-              (first && pass == 0 && ks == 0) ? 0u : 1u);
-    }
-  }
-}
-__device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
-// one fp32 value -> bf16 hi / lo of element (row, k) of the relay-vector operand
-template <int NPASS>
-__device__ __forceinline__ void put_relay_operand(uint8_t* rb, int row, int k, float v) {
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  const uint32_t off = ((uint32_t)k >> 6) * sf::RB_PLANE + sw128_offset((uint32_t)row, (uint32_t)k & 63u);
-  *reinterpret_cast<__nv_bfloat16*>(rb + off) = h;
-  if (NPASS == 3) *reinterpret_cast<__nv_bfloat16*>(rb + 2 * sf::RB_PLANE + off) = __float2bfloat16_rn(v - __bfloat162float(h));
-}
 
 template <int NPASS, bool TRACE>
 __global__ void __launch_bounds__(sf::kThreads, 1)
@@ -652,6 +552,10 @@ using namespace dsc;
 #ifdef DSC_DEBUG_TOOLS
 #include "debug/deepsc_b200_debug.h"
 static bool g_star_trace_on = false;
+namespace dsc { extern unsigned long long* g_pp_trace_host; }
+#endif
+#ifndef DSC_STAR_TWO_TILE_DEFAULT
+#define DSC_STAR_TWO_TILE_DEFAULT 0
 #endif
 
 template <int NPASS, bool TRACE>
@@ -672,6 +576,7 @@ extern "C" int dsc_debug_star_trace(void* device_buffer_768_u64) {
   cudaError_t e = cudaMemcpyToSymbol(dsc::g_star_trace, &p, sizeof(p));
   if (e != cudaSuccess) { set_error("dsc_debug_star_trace: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
   g_star_trace_on = p != nullptr;
+  dsc::g_pp_trace_host = p;
   return DSC_OK;
 }
 #endif
@@ -691,8 +596,10 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
   DSC_REQUIRE((((uintptr_t)packed_wqkv_grouped | (uintptr_t)packed_wo | (uintptr_t)packed_wkv_relay | (uintptr_t)packed_wo_relay |
                 (uintptr_t)packed_wq_relay) & 127u) == 0, "dsc_star_cycles_tc: packed weights must be 128-byte aligned");
   const int skip0 = ((prec & DSC_STAR_FIRST_SAT_DONE) ? 1 : 0) | ((prec & DSC_STAR_NO_FINAL_RELAY) ? 2 : 0);   // kernel flags
+  const int form = prec & (DSC_STAR_FORM_ONE_TILE | DSC_STAR_FORM_TWO_TILE);
   prec &= 255;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_star_cycles_tc: prec must be 1 (bf16x3) or 2 (bf16)");
+  DSC_REQUIRE(form != (DSC_STAR_FORM_ONE_TILE | DSC_STAR_FORM_TWO_TILE), "dsc_star_cycles_tc: pick at most one kernel form");
   DSC_REQUIRE(!(skip0 & 1) || n_cycles >= 2, "dsc_star_cycles_tc: DSC_STAR_FIRST_SAT_DONE needs n_cycles >= 2");
   if (n_sent == 0) return DSC_OK;
   if (n2 == 0) kv2 = kv_e;        // rows are read but masked (lane < n2 is false): any readable [n_sent][64][32][4] floats do
@@ -701,6 +608,11 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
                 reinterpret_cast<const uint8_t*>(packed_wq_relay)};
   cudaStream_t st = as_stream(stream);
   const int n_tiles = n_sent / 4;
+  // two forms, bit-identical results: the one-tile kernel of this file, and the two-tile (half-cycle-apart) kernel of
+  // dsc_star_pp.cu, which is taken when asked for or when DSC_STAR_TWO_TILE_DEFAULT is built in
+  const bool two_tile = (form == DSC_STAR_FORM_TWO_TILE) || (DSC_STAR_TWO_TILE_DEFAULT && form == 0 && n_tiles >= 2 * kSMs);
+  if (two_tile)
+    return launch_star_pp(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, prec == 1 ? 3 : 1, st);
 #ifdef DSC_DEBUG_TOOLS
   if (g_star_trace_on)
     return prec == 1 ? launch_star_fused<3, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st)

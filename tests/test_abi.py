@@ -54,6 +54,10 @@ def test_new_entry_points_validate_before_touching_the_gpu():
     assert rc == -1 and b"n_cycles >= 2" in lib.dsc_last_error()
     rc = lib.dsc_star_cycles_tc(q, q, q, q, None, 0, q, q, q, q, q, q, q, q, 6, 8, 1, None)
     assert rc == -1 and b"multiple of 4" in lib.dsc_last_error()
+    # the two kernel-form flags exclude each other
+    rc = lib.dsc_star_cycles_tc(q, q, q, q, None, 0, q, q, q, q, q, q, q, q, 8, 2,
+                                1 | _lib.STAR_FORM_ONE_TILE | _lib.STAR_FORM_TWO_TILE, None)
+    assert rc == -1 and b"at most one kernel form" in lib.dsc_last_error()
 
 
 def test_product_has_no_cpu_fallback():
