@@ -99,6 +99,8 @@ class StarGreedyDecoder:
 
     def decode(self, received: torch.Tensor, start_idx: int = START_IDX) -> torch.Tensor:
         net, dec, S = self.net, self.dec, self.n
+        if torch.cuda.is_current_stream_capturing():
+            assert received.shape[0] == S, "a captured star decode needs whole 4-sentence tiles"
         if received.shape[0] != S:
             assert received.shape[0] == self.n_real
             received = _pad4(received)
@@ -236,6 +238,6 @@ def greedy_units(net, inp: torch.Tensor, n_units: int, n_std: torch.Tensor, *, c
                     p_scale=p_scale, detector=detector, attack=attack, PNR_dB=PNR_dB)
     if decoder is None:
         decoder = make_decoder(net, inp.shape[0], max_length, graph=False)      # one-shot call: nothing to amortise
-    if isinstance(decoder, StarGreedyDecoder):
-        return decoder.decode(y, start_idx)
+    if isinstance(decoder, StarGreedyDecoder) or (isinstance(decoder, GraphedDecoder) and isinstance(decoder.dec, StarGreedyDecoder)):
+        return decoder.decode(y, start_idx=start_idx)
     return decoder.decode(y, inp, start_idx)

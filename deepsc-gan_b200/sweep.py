@@ -41,7 +41,7 @@ class SweepRunner:
     """Runs blocks of work items on one GPU.  ``units_per_launch`` units are stacked along the batch axis."""
 
     def __init__(self, net, units_per_launch: int, channel: str = "AWGN", detector: int = 0, max_length: int = 30,
-                 seed: int = 0, attack: Optional[str] = None, psr_db: float = -6.0):
+                 seed: int = 0, attack: Optional[str] = None, psr_db: float = -6.0, graph: Optional[bool] = None):
         """``attack="generator"`` (config 4): the perturbation of ``net.generator`` at a fixed perturbation-to-signal
         ratio.  With ||p||_F = 1 the term sqrt(size)*p has unit mean square, so the perturbation power is
         n_std^2 * PNR and PSR_dB = PNR_dB - SNR_dB: at fixed PSR the scale n_std*sqrt(PNR)*sqrt(size)
@@ -49,7 +49,9 @@ class SweepRunner:
         self.net, self.U, self.channel, self.detector = net, units_per_launch, channel, detector
         self.attack, self.psr_db = attack, psr_db
         self.S = units_per_launch * 64
-        self.decoder = engine.make_decoder(net, self.S, max_length)
+        # graph=True: the 30-step decode loop (static shapes, no random numbers) is replayed as ONE CUDA graph per call;
+        # None keeps engine.make_decoder's default (graph for the launch-bound baseline decoder, eager star decoders)
+        self.decoder = engine.make_decoder(net, self.S, max_length, graph=graph)
         self.dev = net.semantic_decoder.embedding.embeddings.device
         self.seed = seed
         self.launch = 0
