@@ -1,0 +1,214 @@
+// Persistent tcgen05 Dense kernel for K = 128 and many rows (the channel codec's 73,408-row layers 128 -> 256 and
+// 128 -> 512, models/transceiver.py:89-90, 103-105): y = act(x @ W + bias), fp32 in HBM, bf16x3 (or bf16) on the tensor cores.
+//
+// The tiled kernel of dsc_gemm_tc.cu gives every 128 x 128 output tile its own CTA, so a 256-wide layer reads and converts
+// every x row twice and nothing overlaps inside a CTA: 1.3-1.5 TB/s.  This layer is HBM-bound (64 KB of x in, 128 KB of y
+// out per 128-row tile against 1.7 us of UMMAs), so here ONE CTA per SM keeps the packed weights of a 256-column slab
+// resident in shared memory (128 KB) and walks its row tiles with three warp roles:
+//   warps 0-7  loader: x rows (fp32) -> registers -> bf16 hi/lo K-major swizzled A operand in shared memory (64 KB, single
+//              buffer); the NEXT tile's rows are already in flight in registers while this tile's UMMAs run;
+//   warp  8    UMMA issuer: 24 (8 for bf16) SS-mode UMMAs M = 128, N <= 256 into one of two TMEM accumulators;
+//   warps 9-12 epilogue: TMEM -> registers -> bias / ReLU -> per-warp shared-memory tile -> y in whole 128-byte row segments,
+//              overlapping the next tile's load + UMMAs.
+// Algorithmic bytes per row: 4 x (K + N) (x read once per 256-column slab, y written once).
+#include "dsc_common.cuh"
+#include "dsc_tc.cuh"
+
+namespace dsc {
+
+using namespace tc;
+
+namespace k128 {
+constexpr int kLoaders = 8, kIssuer = 8, kThreads = 32 * (kLoaders + 1 + 4);   // 8 loader warps, issuer, 4 epilogue warps
+constexpr uint32_t A_PLANE = 128 * 128;       // [part][kb] plane of the A operand: 128 rows x 128 B
+struct Bars { uint64_t b_full, a_full, a_free, acc_full[2], acc_free[2]; };
+}  // namespace k128
+
+template <int NPASS>
+__global__ void __launch_bounds__(k128::kThreads, 1)
+gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ blob, int n_pad, int n0, int bn,
+                            const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int M, int N, int act) {
+  using namespace k128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int parts = (NPASS == 3) ? 2 : 1;
+  const uint32_t b_plane = (uint32_t)bn * 128u;
+  uint8_t* sB = smem;                                   // [part][kb][bn rows][128 B]
+  uint8_t* sA = smem + parts * 2 * 256 * 128;           // [part][kb][128 rows][128 B]
+  float* stage = reinterpret_cast<float*>(sA + parts * 2 * A_PLANE);   // epilogue: 4 warps x [32 rows][36] floats
+  __shared__ __align__(8) k128::Bars bars;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (M + 127) / 128;
+  const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  for (int i = tid; i < 256; i += kThreads) bias_s[i] = (bias != nullptr && i < bn && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
+  if (tid == 0) {
+    mbar_init(&bars.b_full, 1);
+    mbar_init(&bars.a_full, kLoaders);
+    mbar_init(&bars.a_free, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], 4); }
+    fence_barrier_init();
+  }
+  if (warp == kIssuer) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < kLoaders) {
+    // ------------------------------------------------------------------ loader: lane l holds k = 4l..4l+3 of row warp + 8*it
+    const int kb_l = lane >> 4;
+    const uint32_t k_in = (uint32_t)((lane & 15) << 2);
+    float4 v[16];
+    auto load_tile = [&](int t) {
+      const int m0 = t * 128;
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int gr = m0 + warp + kLoaders * it;
+        v[it] = (gr < M) ? ld_stream(reinterpret_cast<const float4*>(x + (int64_t)gr * ldx) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (my_tiles > 0) load_tile(blockIdx.x);
+    for (int i = 0; i < my_tiles; ++i) {
+      if (i > 0) mbar_wait(&bars.a_free, (uint32_t)(i - 1) & 1u);       // the UMMAs of the previous tile have read sA
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        uint32_t h0, l0, h1, l1;
+        split2(v[it].x, v[it].y, h0, l0);
+        split2(v[it].z, v[it].w, h1, l1);
+        const uint32_t off = kb_l * A_PLANE + sw128_offset((uint32_t)(warp + kLoaders * it), k_in);
+        *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
+        if (NPASS == 3) *reinterpret_cast<uint2*>(sA + 2 * A_PLANE + off) = make_uint2(l0, l1);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.a_full);
+      if (i + 1 < my_tiles) load_tile(blockIdx.x + (i + 1) * gridDim.x);   // in flight while this tile's UMMAs run
+    }
+  } else if (warp == kIssuer) {
+    // ------------------------------------------------------------------ weights (once), then the UMMA issuer
+    if (lane == 0 && my_tiles > 0) {
+      mbar_expect_tx(&bars.b_full, parts * 2 * b_plane);
+      for (int p = 0; p < parts; ++p)
+        for (int kb = 0; kb < 2; ++kb)
+          bulk_g2s(sB + (p * 2 + kb) * b_plane, blob + ((size_t)(p * 2 + kb) * n_pad + (size_t)n0) * 128, b_plane, &bars.b_full);
+    }
+    __syncwarp();
+    const bool leader = elect_one();
+    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    const uint32_t idesc = idesc_bf16_f32(128, bn);
+    if (my_tiles > 0) mbar_wait(&bars.b_full, 0);
+    for (int i = 0; i < my_tiles; ++i) {
+      const uint32_t b = (uint32_t)i & 1u, use = (uint32_t)i >> 1;
+      mbar_wait(&bars.a_full, (uint32_t)i & 1u);
+      mbar_wait(&bars.acc_free[b], (use - 1) & 1u);                     // the epilogue drained this accumulator
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int pass = 0; pass < NPASS; ++pass) {
+          const uint32_t pa = (pass == 1) ? 1u : 0u, pb = (pass == 2) ? 1u : 0u;   // hi*hi, lo*hi, hi*lo
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss(tmem_base + b * 256u, smem_desc_sw128(a_base + (pa * 2 + kb) * A_PLANE + ks * 32u),
+                      smem_desc_sw128(b_base + (pb * 2 + kb) * b_plane + ks * 32u), idesc, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&bars.a_free);
+        umma_commit(&bars.acc_full[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warps 9..12 own TMEM lane quarters 1, 2, 3, 0
+    const int quarter = warp & 3;
+    const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
+    for (int i = 0; i < my_tiles; ++i) {
+      const uint32_t b = (uint32_t)i & 1u, use = (uint32_t)i >> 1;
+      const int t = blockIdx.x + i * gridDim.x;
+      mbar_wait(&bars.acc_full[b], use & 1u);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + b * 256u;
+#pragma unroll 1
+      for (int j = 0; j < bn / 32; ++j) {
+        float v[32];
+        tmem_ld32(acc + (uint32_t)(j * 32), v);
+        tmem_ld_wait();
+        if (j + 1 == bn / 32) {                                         // last read of this accumulator
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.acc_free[b]);
+        }
+        // bias / ReLU in registers, then through a per-warp shared-memory tile so that every store instruction writes whole
+        // 128-byte row segments (lane -> row lane >> 3 (+4 per step), columns 4 * (lane & 7) ..): written straight from the
+        // accumulator layout (lane = row) each instruction would touch 32 rows with 16 bytes each
+        const int c0 = n0 + j * 32;
+        float* tile = stage + (warp - kIssuer - 1) * (32 * 36);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 o;
+          o.x = v[q * 4] + bias_s[j * 32 + q * 4];
+          o.y = v[q * 4 + 1] + bias_s[j * 32 + q * 4 + 1];
+          o.z = v[q * 4 + 2] + bias_s[j * 32 + q * 4 + 2];
+          o.w = v[q * 4 + 3] + bias_s[j * 32 + q * 4 + 3];
+          if (act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(tile + lane * 36 + q * 4) = o;
+        }
+        __syncwarp();
+        const int rr = lane >> 3, cc = (lane & 7) * 4;
+        const int col = c0 + cc;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int r = 4 * k + rr;
+          const int grow = t * 128 + quarter * 32 + r;
+          const float4 o = *reinterpret_cast<const float4*>(tile + r * 36 + cc);
+          if (grow < M) {
+            float* dst = y + (int64_t)grow * ldy + col;
+            if (vec_ok && col + 3 < N) {
+              st_stream(reinterpret_cast<float4*>(dst), o);
+            } else {
+              if (col < N) dst[0] = o.x;
+              if (col + 1 < N) dst[1] = o.y;
+              if (col + 2 < N) dst[2] = o.z;
+              if (col + 3 < N) dst[3] = o.w;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kIssuer) tmem_dealloc<512>(tmem_base);
+}
+
+template <int NPASS>
+static int launch_k128(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y, int64_t ldy,
+                       int M, int N, int act, cudaStream_t s) {
+  constexpr int parts = (NPASS == 3) ? 2 : 1;
+  constexpr size_t smem = (size_t)parts * 2 * 256 * 128 + (size_t)parts * 2 * 128 * 128 + 4 * 32 * 36 * 4 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_k128_persistent_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("dsc_linear_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
+    attr_set = true;
+  }
+  const int n_tiles = (M + 127) / 128;
+  const int grid = n_tiles < kSMs ? n_tiles : kSMs;
+  for (int n0 = 0; n0 < n_pad; n0 += 256) {                   // one launch per 256-column slab (x is re-read per slab)
+    const int bn = (n_pad - n0) < 256 ? (n_pad - n0) : 256;
+    gemm_k128_persistent_kernel<NPASS><<<grid, k128::kThreads, smem, s>>>(x, ldx, blob, n_pad, n0, bn, bias, y, ldy, M, N, act);
+  }
+  return check_launch("dsc_linear_tc");
+}
+
+int linear_k128_persistent(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y, int64_t ldy,
+                           int M, int N, int act, int npass, cudaStream_t s) {
+  return npass == 3 ? launch_k128<3>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, s)
+                    : launch_k128<1>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, s);
+}
+
+}  // namespace dsc

@@ -306,6 +306,9 @@ static int launch_gemm_tc(const float* x, int64_t ldx, const uint8_t* blob, int 
   return check_launch("dsc_linear_tc");
 }
 
+int linear_k128_persistent(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y, int64_t ldy,
+                           int M, int N, int act, int npass, cudaStream_t s);   // dsc_gemm_k128.cu
+
 int linear_tc(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, int, int,
               int prec, cudaStream_t) {
   set_error("dsc_linear: prec=%d needs pre-packed weights: call dsc_pack_weight once, then dsc_linear_tc", prec);
@@ -342,6 +345,7 @@ extern "C" int dsc_linear_tc(const float* x, int64_t ldx, const void* packed_w, 
   DSC_REQUIRE((reinterpret_cast<uintptr_t>(packed_w) & 127u) == 0, "dsc_linear_tc: packed weights must be 128-byte aligned");
   DSC_REQUIRE(ldy >= N && (act == 0 || act == 1), "dsc_linear_tc: bad ldy/act");
   const int ts_mode = prec & 16, ts_swap = prec & 32;       // bring-up knobs: A operand staged in TMEM
+  const int prec_flags = prec;                              // | 64: keep the tiled kernel (A/B timing, tests)
   prec &= 15;
   DSC_REQUIRE(prec == 1 || prec == 2, "dsc_linear_tc: prec must be 1 (bf16x3) or 2 (bf16)");
   if (M == 0) return DSC_OK;
@@ -356,6 +360,9 @@ extern "C" int dsc_linear_tc(const float* x, int64_t ldx, const void* packed_w, 
   // many row tiles (the channel codec's 73,408-row layers): 64 KB CTAs, three per SM, so that the phases of different
   // tiles overlap; few tiles (a greedy step's 2,368 rows): one CTA per SM with the whole K = 128 chunk in one pass
   const bool many = (int64_t)((M + TC_BM - 1) / TC_BM) * (n_pad / 128) >= 2 * kSMs;
+  // K = 128 with at least two row tiles per SM: the persistent kernel (weights resident, row tiles streamed)
+  if (K == 128 && row_mod == 0 && (M + TC_BM - 1) / TC_BM >= 2 * kSMs && !(prec_flags & 64))
+    return linear_k128_persistent(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, prec == 1 ? 3 : 1, s);
   if (many)
     return prec == 1 ? launch_gemm_tc<128, 3, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)
                      : launch_gemm_tc<128, 1, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s);

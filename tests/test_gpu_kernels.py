@@ -561,3 +561,27 @@ def test_target_tail_fused(L, dev, prec, tol):
     cache = kv2i.view(Mrows, 64, 32, 4)
     assert torch.equal(cache[:, :, 9, :].reshape(Mrows, 256), rows)
     assert float(cache[:, :, 8, :].abs().max()) == 0.0 and float(cache[:, :, 10, :].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,act", [(256, 1), (512, 1), (384, 0), (100, 0)])
+@pytest.mark.parametrize("prec,tol", [(1, 2e-5), (2, 1e-2)])
+def test_persistent_k128_dense_matches_fp64_and_the_tiled_kernel(L, dev, N, act, prec, tol):
+    """The persistent K = 128 Dense kernel (dsc_gemm_k128.cu: taken from two 128-row tiles per SM up, i.e. the channel
+    codec's 73,408-row layers) against fp64, and against the tiled kernel (prec | 64; its K-block-major accumulation order
+    differs, so agreement is to rounding, not bit for bit).  40,011 rows: ragged last tile, 3 tiles on some SMs, 2 on others."""
+    M, K = 40011, 128
+    g = torch.Generator().manual_seed(N + act)
+    x = torch.randn(M, K, generator=g).to(dev)
+    w = (torch.randn(K, (N + 3) // 4 * 4, generator=g) * 0.1).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    y = torch.full((M, N), float("nan"), device=dev)
+    L.linear(x, w, b, act=act, n=N, prec=prec, out=y)
+    y_tiled = torch.empty((M, N), device=dev)
+    L.linear(x, w, b, act=act, n=N, prec=prec | 64, out=y_tiled)
+    ref = x.double() @ w[:, :N].double() + b.double()
+    if act:
+        ref = ref.clamp_min(0)
+    torch.cuda.synchronize()
+    assert not torch.isnan(y).any()
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < tol
+    assert float((y - y_tiled).abs().max() / ref.abs().max()) < 2 * tol
