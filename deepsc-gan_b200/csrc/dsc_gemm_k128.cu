@@ -8,7 +8,7 @@
 //   warps 0-7  loader: x rows (fp32) -> registers -> bf16 hi/lo K-major swizzled A operand in shared memory (64 KB, single
 //              buffer); the NEXT tile's rows are already in flight in registers while this tile's UMMAs run;
 //   warp  8    UMMA issuer: 24 (8 for bf16) SS-mode UMMAs M = 128, N <= 256 into one of two TMEM accumulators;
-//   warps 9-12 epilogue: TMEM -> registers -> bias / ReLU -> per-warp shared-memory tile -> y in whole 128-byte row segments,
+//   warps 9-16 epilogue: TMEM -> registers -> bias / ReLU -> y (two warps per TMEM lane quarter, alternate 32-column groups),
 //              overlapping the next tile's load + UMMAs.
 // Algorithmic bytes per row: 4 x (K + N) (x read once per 256-column slab, y written once).
 #include "dsc_common.cuh"
@@ -19,7 +19,7 @@ namespace dsc {
 using namespace tc;
 
 namespace k128 {
-constexpr int kLoaders = 8, kIssuer = 8, kThreads = 32 * (kLoaders + 1 + 4);   // 8 loader warps, issuer, 4 epilogue warps
+constexpr int kLoaders = 8, kIssuer = 8, kEpi = 8, kThreads = 32 * (kLoaders + 1 + kEpi);   // 8 loader warps, issuer, 8 epilogue warps
 constexpr uint32_t A_PLANE = 128 * 128;       // [part][kb] plane of the A operand: 128 rows x 128 B
 struct Bars { uint64_t b_full, a_full, a_free, acc_full[2], acc_free[2]; };
 }  // namespace k128
@@ -35,10 +35,10 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
   const uint32_t b_plane = (uint32_t)bn * 128u;
   uint8_t* sB = smem;                                   // [part][kb][bn rows][128 B]
   uint8_t* sA = smem + parts * 2 * 256 * 128;           // [part][kb][128 rows][128 B]
-  float* stage = reinterpret_cast<float*>(sA + parts * 2 * A_PLANE);   // epilogue: 4 warps x [32 rows][36] floats
+  float* stage = reinterpret_cast<float*>(sA + parts * 2 * A_PLANE);   // epilogue: 8 warps x [32 rows][32] floats, XOR-swizzled
   __shared__ __align__(8) k128::Bars bars;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[256];
+  __shared__ __align__(16) float bias_s[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (M + 127) / 128;
@@ -48,7 +48,7 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
     mbar_init(&bars.b_full, 1);
     mbar_init(&bars.a_full, kLoaders);
     mbar_init(&bars.a_free, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kEpi); }
     fence_barrier_init();
   }
   if (warp == kIssuer) tmem_alloc<512>(&tmem_base_s);
@@ -122,8 +122,9 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: warps 9..12 own TMEM lane quarters 1, 2, 3, 0
-    const int quarter = warp & 3;
+    // ------------------------------------------------------------------ epilogue: warps 9..16, TMEM lane quarter = warp & 3, two
+    // warps per quarter taking alternate 32-column groups (one warp per scheduler was latency-bound: ~9 us per tile)
+    const int quarter = warp & 3, e_half = (warp - kIssuer - 1) >> 2;
     const bool vec_ok = ((ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
     for (int i = 0; i < my_tiles; ++i) {
       const uint32_t b = (uint32_t)i & 1u, use = (uint32_t)i >> 1;
@@ -132,38 +133,40 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
       tc_fence_after();
       const uint32_t acc = tmem_base + ((uint32_t)(quarter * 32) << 16) + b * 256u;
 #pragma unroll 1
-      for (int j = 0; j < bn / 32; ++j) {
+      for (int j = e_half; j < bn / 32; j += 2) {
         float v[32];
         tmem_ld32(acc + (uint32_t)(j * 32), v);
         tmem_ld_wait();
-        if (j + 1 == bn / 32) {                                         // last read of this accumulator
+        if (j + 2 >= bn / 32) {                                         // this warp's last read of the accumulator
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.acc_free[b]);
         }
-        // bias / ReLU in registers, then through a per-warp shared-memory tile so that every store instruction writes whole
-        // 128-byte row segments (lane -> row lane >> 3 (+4 per step), columns 4 * (lane & 7) ..): written straight from the
-        // accumulator layout (lane = row) each instruction would touch 32 rows with 16 bytes each
+        // bias / ReLU in registers, then through a per-warp XOR-swizzled shared-memory tile so that every store instruction
+        // writes whole 128-byte row segments (lane -> row 4k + (lane >> 3), columns 4 * (lane & 7) ..).  Written straight from
+        // the accumulator layout (lane = row) an instruction touches 32 rows with 16 bytes each: the same speed while y stays
+        // in L2 (73,408 x 256), 7-25 % slower once y goes to HBM (N = 512, or 4 x the rows).
         const int c0 = n0 + j * 32;
-        float* tile = stage + (warp - kIssuer - 1) * (32 * 36);
+        float* tile = stage + (warp - kIssuer - 1) * (32 * 32);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[j * 32 + q * 4]);
           float4 o;
-          o.x = v[q * 4] + bias_s[j * 32 + q * 4];
-          o.y = v[q * 4 + 1] + bias_s[j * 32 + q * 4 + 1];
-          o.z = v[q * 4 + 2] + bias_s[j * 32 + q * 4 + 2];
-          o.w = v[q * 4 + 3] + bias_s[j * 32 + q * 4 + 3];
+          o.x = v[q * 4] + b4.x;
+          o.y = v[q * 4 + 1] + b4.y;
+          o.z = v[q * 4 + 2] + b4.z;
+          o.w = v[q * 4 + 3] + b4.w;
           if (act == 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(tile + lane * 36 + q * 4) = o;
+          *reinterpret_cast<float4*>(tile + lane * 32 + ((q ^ (lane & 7)) << 2)) = o;
         }
         __syncwarp();
-        const int rr = lane >> 3, cc = (lane & 7) * 4;
-        const int col = c0 + cc;
+        const int rr = lane >> 3, cg = lane & 7;
+        const int col = c0 + cg * 4;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int r = 4 * k + rr;
           const int grow = t * 128 + quarter * 32 + r;
-          const float4 o = *reinterpret_cast<const float4*>(tile + r * 36 + cc);
+          const float4 o = *reinterpret_cast<const float4*>(tile + r * 32 + ((cg ^ (r & 7)) << 2));
           if (grow < M) {
             float* dst = y + (int64_t)grow * ldy + col;
             if (vec_ok && col + 3 < N) {
@@ -189,7 +192,7 @@ template <int NPASS>
 static int launch_k128(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y, int64_t ldy,
                        int M, int N, int act, cudaStream_t s) {
   constexpr int parts = (NPASS == 3) ? 2 : 1;
-  constexpr size_t smem = (size_t)parts * 2 * 256 * 128 + (size_t)parts * 2 * 128 * 128 + 4 * 32 * 36 * 4 + 1024;
+  constexpr size_t smem = (size_t)parts * 2 * 256 * 128 + (size_t)parts * 2 * 128 * 128 + k128::kEpi * 32 * 32 * 4 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_k128_persistent_kernel<NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

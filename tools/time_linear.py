@@ -12,7 +12,7 @@ def timed(fn,reps=10,inner=20):
         for _ in range(inner): fn()
         b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b)*1e3/inner)
     ts.sort(); return ts[len(ts)//2]
-for M,K,N in ((73408,128,256),(73408,128,512),(73408,512,128),(73408,256,16),(2368,128,384)):
+for M,K,N in ((73408,128,256),(293632,128,256),(73408,128,512),(73408,512,128),(73408,256,16),(2368,128,384)):
     x=torch.randn(M,K,device=dev); w=torch.randn(K,(N+3)//4*4,device=dev)*0.1; b=torch.randn(N,device=dev); y=torch.empty(M,N,device=dev)
     t0=timed(lambda: L.linear(x,w,b,act=1,n=N,prec=1|64,out=y))
     t=timed(lambda: L.linear(x,w,b,act=1,n=N,prec=1,out=y))
