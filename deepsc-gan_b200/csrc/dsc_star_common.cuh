@@ -32,7 +32,10 @@ namespace sf {
 // 32 KB stages, as the two-tile kernel does to fit its ATT buffer) was measured on the one-tile kernel at ring depths 3..6:
 // 5 % SLOWER at every depth (the mid-job wait and second commit cost more than the L1 that 3 x 32 KB frees).
 constexpr uint32_t RSTAGE = 2 * 128 * 128;                    // the two-tile kernel's ring stage (half a chunk)
-constexpr int STAGES = 2;                                     // one-tile kernel: whole chunks; 3 stages are 5 % slower
+#ifndef SF_STAGES
+#define SF_STAGES 2
+#endif
+constexpr int STAGES = SF_STAGES;                             // one-tile kernel: whole chunks; 3 stages are 5 % slower
 constexpr uint32_t STAGE_BYTES = 4 * 128 * 128;               // largest chunk: 4 planes x 128 rows x 128 B = 64 KB
 constexpr uint32_t RB_PLANE = 16 * 128;                       // relay-vector operand: one (part, kb) plane = 16 rows x 128 B
 constexpr uint32_t RB_BYTES = 4 * RB_PLANE;                   // 8 KB behind the ring

@@ -60,7 +60,23 @@ namespace dsc {
 using namespace tc;
 
 namespace sf {
-constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = 576;
+// Register reallocation: 20 warps = 5 warpgroups (16 compute warps; issuer, producer and two idle warps).  At launch every
+// thread has 96 registers (65,536 / 640); the last warpgroup gives back all but 32 (setmaxnreg.dec) and the compute
+// warpgroups take them (setmaxnreg.inc 112: (112 - 96) x 512 = (96 - 32) x 128, the pool is exact).  At 112 registers the
+// compute code has no local-memory traffic at all (96: 140 B of spill stores / 212 B of loads per thread, whose misses go to
+// L2 because the key streams thrash L1): 447 -> 422 us per 8-cycle launch, a greedy-step launch 394 -> 369 us.
+// SF_PRED_KV2: lanes whose target-key row is masked (lane >= n2) do not fetch it.
+#ifndef SF_SETMAXNREG
+#define SF_SETMAXNREG 1
+#endif
+#ifndef SF_COMPUTE_REGS
+#define SF_COMPUTE_REGS 112
+#define SF_SIDE_REGS 32
+#endif
+#ifndef SF_PRED_KV2
+#define SF_PRED_KV2 1
+#endif
+constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = SF_SETMAXNREG ? 640 : 576;
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
 constexpr uint32_t ACC_Q = ACC1 + 96;                         // J8's 16 columns: behind the 96 columns of a QKV job
 // Issue order of a cycle: J0..J3, then J8 (the query q' of THIS cycle's relay attention, from the previous cycle's s';
@@ -148,7 +164,11 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
   const uint32_t tmem_base = tmem_base_s;
   const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-  if (warp == kProdWarp) {
+#if SF_SETMAXNREG
+  if (warp >= kCompute) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(SF_SIDE_REGS));
+#endif
+  if (warp > kProdWarp) {
+  } else if (warp == kProdWarp) {
     // ------------------------------------------------------------------ weight producer
     if (lane == 0) {
       uint32_t n = 0;                                   // chunks issued so far
@@ -219,6 +239,9 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
     }
   } else {
     // ------------------------------------------------------------------ compute warps (16)
+#if SF_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(SF_COMPUTE_REGS));
+#endif
     // quarter = TMEM lane quarter = sentence of the tile; sub = column quarter (32 of the 128 columns, = heads 2*sub,
     // 2*sub+1 of the relay attention).  In the QKV phase sub also picks the accumulator: warps with sub < 2 take the
     // even head pairs (ACC0), the others the odd ones (ACC1), head 2g + (sub & 1) each.
@@ -404,7 +427,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           const bool has2 = lane < n2;
           float4 k2[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) k2[i] = __ldg(kv2 + i * 32);
+          for (int i = 0; i < 8; ++i) k2[i] = (!SF_PRED_KV2 || has2) ? __ldg(kv2 + i * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
           float w1[2], w2[2];
           compute_warps_sync();                                      // q' (written feature-major by the J8 epilogue) is complete
           wait_acc(1);
@@ -433,7 +456,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           }
           DSC_TR(warp ? 512 : 256);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) k2[i] = __ldg(kv2 + (32 + i) * 32);      // the values take the keys' registers
+          for (int i = 0; i < 8; ++i) k2[i] = (!SF_PRED_KV2 || has2) ? __ldg(kv2 + (32 + i) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);      // the values take the keys' registers
           free_acc(1);
           wait_acc(0);
 #pragma unroll

@@ -1,0 +1,1 @@
+for v in "$@"; do echo "== $v"; DSC_LIB_PATH=deepsc-gan_b200/csrc/_var/lib_$v.so timeout 100 python tools/pp_check.py time-only 2>&1 | grep "one-tile"; done
