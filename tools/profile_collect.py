@@ -33,6 +33,12 @@ KEEP = [
     "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio", "smsp__average_warp_latency_issue_stalled_imc_miss.ratio",
     "smsp__average_warp_latency_issue_stalled_not_selected.ratio", "smsp__average_warp_latency_issue_stalled_selected.ratio",
     "smsp__average_warp_latency_issue_stalled_drain.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes.sum.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
     "local_load_bytes", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
 ]
 
@@ -62,13 +68,24 @@ def main(tag, name):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), os.path.join(out, f"{tag}_launches.csv")],
                        capture_output=True, text=True)
     with open(os.path.join(prof, f"{name}_launches_bench_step.txt"), "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv python bench.py --steps 2 --warmup 3\n"
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --train-steps 0\n"
                 "# (per-launch times are cold-cache and serialised: the SHARE per kernel is what is compared with bench.py's roofline.share_of_step)\n")
         f.write(r.stdout.replace(out + "/", "gpurun_out/"))
     summarise(os.path.join(out, f"{tag}_star_fused.ncu-rep"),
               "star_fused_kernel<3>: tools/prof_star.py 1 2368 8 (2,368 sentences = 592 tiles, 8 cycles, n2 = 17), B200", os.path.join(prof, f"{name}_ncu_star_fused.txt"))
-    summarise(os.path.join(out, f"{tag}_vocab.ncu-rep"),
-              "vocab_argmax_tc_kernel<3>: tools/prof_vocab.py (2,368 rows x 22,234 vocabulary entries), B200", os.path.join(prof, f"{name}_ncu_vocab_argmax.txt"))
+    # the other kernels of a bench step (tools/profile_round.sh `kernels`: one capture each out of `bench.py --steps 1 --warmup 1`)
+    for f, title in (("vocab_argmax_tc_", "vocab_argmax_tc_kernel<3>: one greedy step of bench.py (2,368 rows x 22,234 vocabulary entries)"),
+                     ("tar_tail_", "tar_tail_kernel<3>: Dense + residual + LayerNorm + relay k|v projection + key-cache write of a greedy step (2,368 rows)"),
+                     ("mha_decode_attention_", "mha_decode_attention_kernel: single-query attention of a greedy step (2,368 sentences x 8 heads)"),
+                     ("add_layernorm_", "add_layernorm_kernel: the two final LayerNorms of a greedy step (2,368 rows)"),
+                     ("gemm_k128_", "gemm_k128_persistent_kernel<3>: tools/time_linear.py, 73,408 x 128 -> 256 Dense + ReLU"),
+                     ("gemm_tc_kernel_128__3__2", "gemm_tc_kernel<128,3,2>: the q|k|v projection of a greedy step (2,368 x 128 -> 384)")):
+        rep = os.path.join(out, f"{tag}_k_{f}.ncu-rep")
+        if os.path.exists(rep):
+            summarise(rep, title + ", B200", os.path.join(prof, f"{name}_ncu_{f.strip('_')}.txt"))
+    for extra in ("smoke.log", "bench.err"):
+        if os.path.exists(os.path.join(out, f"{tag}_{extra}")):
+            shutil.copy(os.path.join(out, f"{tag}_{extra}"), os.path.join(prof, f"{name}_{extra.replace('.', '_run.') if extra == 'bench.err' else extra}"))
     log = os.path.join(out, f"{tag}_pytest_gpu.log")
     if os.path.exists(log):
         shutil.copy(log, os.path.join(prof, f"{name}_pytest_gpu.log"))
