@@ -66,6 +66,10 @@ namespace sf {
 // compute code has no local-memory traffic at all (96: 140 B of spill stores / 212 B of loads per thread, whose misses go to
 // L2 because the key streams thrash L1): 447 -> 422 us per 8-cycle launch, a greedy-step launch 394 -> 369 us.
 // SF_PRED_KV2: lanes whose target-key row is masked (lane >= n2) do not fetch it.
+// SF_RELAY_PAIR: the relay attention reduces both heads of a warp together - the two softmax reductions and the two 31-shuffle
+// reduce-scatters are independent dependency chains, interleaved instruction by instruction (the loop form serialises them:
+// shuffles are not reordered across the tcgen05.ld of the second head).  With 112 registers this no longer spills (round 1: it
+// did, and was 5 % slower): 419 -> 409 us per 8-cycle launch, greedy-step launch 368 -> 359 us, results bit-identical.
 #ifndef SF_SETMAXNREG
 #define SF_SETMAXNREG 1
 #endif
@@ -75,6 +79,9 @@ namespace sf {
 #endif
 #ifndef SF_PRED_KV2
 #define SF_PRED_KV2 1
+#endif
+#ifndef SF_RELAY_PAIR
+#define SF_RELAY_PAIR 1
 #endif
 constexpr int kCompute = 16, kMmaWarp = 16, kProdWarp = 17, kThreads = SF_SETMAXNREG ? 640 : 576;
 constexpr uint32_t ACC0 = 0, ACC1 = 128, AX_HI = 256, AX_LO = 320, AT_HI = 384, AT_LO = 448;
@@ -431,6 +438,91 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           float w1[2], w2[2];
           compute_warps_sync();                                      // q' (written feature-major by the J8 epilogue) is complete
           wait_acc(1);
+#if SF_RELAY_PAIR
+          // both heads of the warp in one pass: the two softmax reductions (and below the two 31-shuffle reduce-scatters) are
+          // independent dependency chains, interleaved instruction by instruction; same arithmetic per head as the loop form
+          {
+            float d1[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float k[16];
+              tmem_ld16(lane_addr + ACC1 + sub * 32 + h * 16, k);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 qq = reinterpret_cast<const float4*>(my_q + h * 16)[q4];
+                d1[h] = fmaf(qq.x, k[4*q4], d1[h]); d1[h] = fmaf(qq.y, k[4*q4+1], d1[h]);
+                d1[h] = fmaf(qq.z, k[4*q4+2], d1[h]); d1[h] = fmaf(qq.w, k[4*q4+3], d1[h]);
+                const float4 kk = k2[h * 4 + q4];
+                d2[h] = fmaf(qq.x, kk.x, d2[h]); d2[h] = fmaf(qq.y, kk.y, d2[h]); d2[h] = fmaf(qq.z, kk.z, d2[h]); d2[h] = fmaf(qq.w, kk.w, d2[h]);
+              }
+            }
+            d1[0] *= 0.25f; d1[1] *= 0.25f;
+            d2[0] = has2 ? d2[0] * 0.25f : -3.4e38f;
+            d2[1] = has2 ? d2[1] * 0.25f : -3.4e38f;
+            float m0 = fmaxf(d1[0], d2[0]), m1 = fmaxf(d1[1], d2[1]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float t0 = __shfl_xor_sync(0xffffffffu, m0, o), t1 = __shfl_xor_sync(0xffffffffu, m1, o);
+              m0 = fmaxf(m0, t0); m1 = fmaxf(m1, t1);
+            }
+            const float e10 = expf(d1[0] - m0), e20 = has2 ? expf(d2[0] - m0) : 0.f;
+            const float e11 = expf(d1[1] - m1), e21 = has2 ? expf(d2[1] - m1) : 0.f;
+            float s0 = e10 + e20, s1 = e11 + e21;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float t0 = __shfl_xor_sync(0xffffffffu, s0, o), t1 = __shfl_xor_sync(0xffffffffu, s1, o);
+              s0 += t0; s1 += t1;
+            }
+            const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+            w1[0] = e10 * i0; w2[0] = e20 * i0;
+            w1[1] = e11 * i1; w2[1] = e21 * i1;
+          }
+          DSC_TR(warp ? 512 : 256);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) k2[i] = (!SF_PRED_KV2 || has2) ? __ldg(kv2 + (32 + i) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);      // the values take the keys' registers
+          free_acc(1);
+          wait_acc(0);
+          {
+            float p[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float v[16];
+              tmem_ld16(lane_addr + ACC0 + sub * 32 + h * 16, v);
+              tmem_ld_wait();
+              if (h == 1) free_acc(0);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                float4 vv = k2[h * 4 + q4];
+                if (!has2) vv = make_float4(0.f, 0.f, 0.f, 0.f);                // masked rows may hold anything
+                p[h*16 + 4*q4]     = fmaf(w1[h], v[4*q4],     w2[h] * vv.x);
+                p[h*16 + 4*q4 + 1] = fmaf(w1[h], v[4*q4 + 1], w2[h] * vv.y);
+                p[h*16 + 4*q4 + 2] = fmaf(w1[h], v[4*q4 + 2], w2[h] * vv.z);
+                p[h*16 + 4*q4 + 3] = fmaf(w1[h], v[4*q4 + 3], w2[h] * vv.w);
+              }
+            }
+            // sum over the 32 key lanes, both heads at once: fold the half-warps, then reduce-scatter 16 values over 16 lanes
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p[i] += __shfl_xor_sync(0xffffffffu, p[i], 16);
+#pragma unroll
+            for (int off = 8, n = 8; off >= 1; off >>= 1, n >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < n; ++i) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const float send = upper ? p[h*16 + i] : p[h*16 + i + n];
+                  const float keep = upper ? p[h*16 + i + n] : p[h*16 + i];
+                  p[h*16 + i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+            }
+            if (lane < 16) {
+              put_relay_operand<NPASS>(rb, quarter, sub * 32 + lane, p[0]);
+              put_relay_operand<NPASS>(rb, quarter, sub * 32 + 16 + lane, p[16]);
+            }
+          }
+#else
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             // (both heads in one 32-column pass with interleaved reductions was tried: more spills, 5 % slower)
@@ -492,6 +584,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
             // previous cycle, has completed: every warp drained that accumulator)
             if (lane < 16) put_relay_operand<NPASS>(rb, quarter, sub * 32 + h * 16 + lane, p[0]);
           }
+#endif
           fence_async_smem();
           warp_arrive(&bars.t_ready, 1);
         }
