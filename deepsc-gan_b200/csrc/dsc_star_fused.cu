@@ -80,6 +80,14 @@ namespace sf {
 #ifndef SF_PRED_KV2
 #define SF_PRED_KV2 1
 #endif
+#ifndef SF_ISSUER_SPIN
+#define SF_ISSUER_SPIN 1
+#endif
+#if SF_ISSUER_SPIN
+#define SF_ISSUER_WAIT mbar_wait_spin
+#else
+#define SF_ISSUER_WAIT mbar_wait
+#endif
 #ifndef SF_RELAY_PAIR
 #define SF_RELAY_PAIR 1
 #endif
@@ -211,13 +219,13 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
           for (int ji = 0; ji < jobs; ++ji, ++n) {
             const int j = seq.job_at(c, ji);
             const uint32_t st = n % STAGES, b = (j < 7) ? ((uint32_t)j & 1u) : 0u;                    // J7 -> ACC0
-            if (j == 0 || j == 5) { mbar_wait(&bars.x_ready, xr & 1); ++xr; }          // X staged / X' restaged
-            if (j == 7 || j == 8) { mbar_wait(&bars.t_ready, tr & 1); ++tr; }          // att_r / s' staged
-            if (j == 4) { mbar_wait(&bars.ta_ready, ta & 1); ++ta; }                   // first half of ATT staged
-            mbar_wait(&bars.w_full[st], (n / STAGES) & 1);
+            if (j == 0 || j == 5) { SF_ISSUER_WAIT(&bars.x_ready, xr & 1); ++xr; }          // X staged / X' restaged
+            if (j == 7 || j == 8) { SF_ISSUER_WAIT(&bars.t_ready, tr & 1); ++tr; }          // att_r / s' staged
+            if (j == 4) { SF_ISSUER_WAIT(&bars.ta_ready, ta & 1); ++ta; }                   // first half of ATT staged
+            SF_ISSUER_WAIT(&bars.w_full[st], (n / STAGES) & 1);
             if (j != 8) {                                                              // J8 has its own columns (ACC_Q); every
-              if (b) { mbar_wait(&bars.acc_free[1], (use1 - 1) & 1); ++use1; }         // warp read the previous q' before it
-              else   { mbar_wait(&bars.acc_free[0], (use0 - 1) & 1); ++use0; }         // freed this cycle's first accumulators
+              if (b) { SF_ISSUER_WAIT(&bars.acc_free[1], (use1 - 1) & 1); ++use1; }         // warp read the previous q' before it
+              else   { SF_ISSUER_WAIT(&bars.acc_free[0], (use0 - 1) & 1); ++use0; }         // freed this cycle's first accumulators
             }
             tc_fence_after();
             if (t == 0) DSC_TR(0);
@@ -231,7 +239,7 @@ star_fused_kernel(const float* __restrict__ XI0, const float* __restrict__ S0, c
               else issue_group<NPASS, 128>(tmem_base, acc, AX_HI, AX_LO, bb, 128u * 128u, 0u);
             }
             if (j == 4) {                                     // second half of ATT (heads 4..7), then the K-block 1 UMMAs
-              mbar_wait(&bars.t_ready, tr & 1); ++tr;
+              SF_ISSUER_WAIT(&bars.t_ready, tr & 1); ++tr;
               tc_fence_after();
               if (leader) issue_group_kb<NPASS, 128>(tmem_base, acc, AT_HI, AT_LO, bb, 128u * 128u, 1, false);
             }
