@@ -38,6 +38,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// non-blocking test: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // spinning form (no suspend-time hint): for a warp whose wake-up latency is on the critical path and whose polling costs
 // nothing that matters (the single UMMA issuer warp)
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
