@@ -39,9 +39,9 @@ UNIT = "sentences/s"
 SNRS = list(range(19))
 # dram__bytes_read.sum + dram__bytes_write.sum of one star_fused_kernel<3> launch (8 cycles) from the `ncu --set full`
 # capture summarised in profiles/ (keyed by sentences per launch); null when no capture exists for the size that ran
-ROOFLINE_TRAFFIC_BYTES = {2368: 177657088 + 23527168}   # profiles/r02_ncu_star_fused.txt (full 8-cycle launch, n2 = 17)
+ROOFLINE_TRAFFIC_BYTES = {2368: 177608704 + 24980992}   # profiles/r02_ncu_star_fused.txt (full 8-cycle launch, n2 = 17)
 # sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active of the same capture (the kernel at its own clock)
-NCU_TENSOR_ACTIVE_PCT = {2368: 41.6}
+NCU_TENSOR_ACTIVE_PCT = {2368: 43.2}
 
 
 def load_peaks():
