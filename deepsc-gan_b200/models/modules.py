@@ -163,8 +163,12 @@ class LayerNormalization(nn.Module):
 
 
 def _as_ids(x: torch.Tensor) -> torch.Tensor:
+    """int32 ids with unit stride along the sentence; the row stride is free (dsc_embed takes it), so the one-column slice
+    a greedy step embeds is passed as a view instead of being copied by a separate kernel every step."""
     if x.dtype != torch.int32:
         x = x.to(torch.int32)
+    if x.dim() == 2 and (x.shape[1] == 1 or x.stride(1) == 1):
+        return x
     return x.contiguous()
 
 
