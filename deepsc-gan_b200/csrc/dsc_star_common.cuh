@@ -175,8 +175,8 @@ __device__ __forceinline__ void issue_group_kb2(uint32_t tmem_base, uint32_t acc
   }
 }
 
-// the two forms of the fused star layer behind dsc_star_cycles_tc (dsc_star_fused.cu: one tile per CTA at a time;
-// dsc_star_pp.cu: two tiles per CTA half a cycle apart)
+// debug-tools library only: the experimental two-tile form of the fused star layer (debug/dsc_star_pp.cu: two tiles per CTA
+// half a cycle apart; dsc_star_fused.cu is the product's one-tile kernel)
 int launch_star_pp(const float* xi0, const float* s0, const float* q0, const float* kvei, const float* kv2i, int n2,
                    const sf::Weights& w, const float* bias_o, const float* bias_r, float* xrow, int n_tiles, int n_cycles,
                    int flags, int npass, cudaStream_t s);

@@ -678,9 +678,7 @@ using namespace dsc;
 static bool g_star_trace_on = false;
 namespace dsc { extern unsigned long long* g_pp_trace_host; }
 #endif
-#ifndef DSC_STAR_TWO_TILE_DEFAULT
-#define DSC_STAR_TWO_TILE_DEFAULT 0
-#endif
+
 
 template <int NPASS, bool TRACE>
 static int launch_star_fused(const float* xi0, const float* s0, const float* q0, const float* kvei, const float* kv2i, int n2,
@@ -732,11 +730,15 @@ extern "C" int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const f
                 reinterpret_cast<const uint8_t*>(packed_wq_relay)};
   cudaStream_t st = as_stream(stream);
   const int n_tiles = n_sent / 4;
-  // two forms, bit-identical results: the one-tile kernel of this file, and the two-tile (half-cycle-apart) kernel of
-  // dsc_star_pp.cu, which is taken when asked for or when DSC_STAR_TWO_TILE_DEFAULT is built in
-  const bool two_tile = (form == DSC_STAR_FORM_TWO_TILE) || (DSC_STAR_TWO_TILE_DEFAULT && form == 0 && n_tiles >= 2 * kSMs);
-  if (two_tile)
+  // The product library has ONE form: the one-tile kernel of this file.  The two-tile (half-cycle-apart) kernel of
+  // debug/dsc_star_pp.cu - bit-identical results, measured 0-2 % faster at 4 tiles per SM before this kernel's register
+  // reallocation and slower since - is an experiment kept in the debug-tools library only.
+#ifdef DSC_DEBUG_TOOLS
+  if (form == DSC_STAR_FORM_TWO_TILE)
     return launch_star_pp(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, prec == 1 ? 3 : 1, st);
+#else
+  DSC_REQUIRE(form != DSC_STAR_FORM_TWO_TILE, "dsc_star_cycles_tc: the two-tile form lives in libdeepsc_b200_debug.so only");
+#endif
 #ifdef DSC_DEBUG_TOOLS
   if (g_star_trace_on)
     return prec == 1 ? launch_star_fused<3, true>(x_tile0, s0, q0, kv_e, kv2, n2, w, bias_o, bias_o_relay, x_rowmajor, n_tiles, n_cycles, skip0, st)

@@ -116,10 +116,10 @@ int dsc_star_kv2_put(const float* vals, float* kv2, int row_index, int n_sent, v
  * predictions[:, -1:]), so the relay half of the LAST cycle is not run: row 31 of x_rowmajor is the relay node before its last update. */
 #define DSC_STAR_FIRST_SAT_DONE 0x100
 #define DSC_STAR_NO_FINAL_RELAY 0x200
-/* Kernel form (results are bit-identical).  Default: the one-tile kernel (a CTA works on one 4-sentence tile at a time).
- * prec | DSC_STAR_FORM_TWO_TILE runs the two-tile kernel (dsc_star_pp.cu): each CTA keeps two tiles half a cycle apart so
- * that one tile's UMMAs run under the other's register work; measured 0-2 % faster at 4 tiles per SM, so it is
- * opt-in.  DSC_STAR_FORM_ONE_TILE forces the default explicitly. */
+/* Kernel form.  The library has one form, the one-tile kernel (a CTA works on one 4-sentence tile at a time);
+ * DSC_STAR_FORM_ONE_TILE names it explicitly.  DSC_STAR_FORM_TWO_TILE is honoured by the debug-tools library only
+ * (libdeepsc_b200_debug.so: an experimental kernel that keeps two tiles per CTA half a cycle apart, bit-identical
+ * results); the product library rejects it with DSC_ERR_BAD_ARG. */
 #define DSC_STAR_FORM_ONE_TILE 0x400
 #define DSC_STAR_FORM_TWO_TILE 0x800
 int dsc_star_cycles_tc(const float* x_tile0, const float* s0, const float* q0, const float* kv_e,

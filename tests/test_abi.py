@@ -58,6 +58,9 @@ def test_new_entry_points_validate_before_touching_the_gpu():
     rc = lib.dsc_star_cycles_tc(q, q, q, q, None, 0, q, q, q, q, q, q, q, q, 8, 2,
                                 1 | _lib.STAR_FORM_ONE_TILE | _lib.STAR_FORM_TWO_TILE, None)
     assert rc == -1 and b"at most one kernel form" in lib.dsc_last_error()
+    # the product library has one kernel form: the experimental two-tile kernel is in the debug-tools library only
+    rc = lib.dsc_star_cycles_tc(q, q, q, q, None, 0, q, q, q, q, q, q, q, q, 8, 2, 1 | _lib.STAR_FORM_TWO_TILE, None)
+    assert rc == -1 and b"libdeepsc_b200_debug.so" in lib.dsc_last_error()
 
 
 def test_product_has_no_cpu_fallback():

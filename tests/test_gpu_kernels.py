@@ -140,74 +140,6 @@ def test_star_cycle_kernels_match_literal_oracle(L, dev, n2, prec, tol, monkeypa
     assert rel_err(x3[:, :31], h_ref3) < 4 * tol and rel_err(x3[:, 31], s_ref3) < 4 * tol
 
 
-@pytest.mark.parametrize("prec,tol", [(1, 1e-4), (2, 5e-2)])
-@pytest.mark.parametrize("n2", [0, 17])
-def test_two_tile_star_kernel_matches_literal_oracle(L, dev, n2, prec, tol, monkeypatch):
-    """The two-tile form of the fused star layer (dsc_star_pp.cu, DSC_STAR_FORM_TWO_TILE) against the same literal oracle
-    as the default one-tile form, on 3 tiles (one CTA, slots A and B, a second tile in slot A)."""
-    import deepsc_gan_b200.models.modules as M
-    monkeypatch.setattr(M, "PREC", prec)
-    monkeypatch.setattr(L, "STAR_FORM", L.STAR_FORM_TWO_TILE)
-    P = _cases.params("Transeiver_Star", gain=3.0)
-    pre = "semantic_decoder/dec_layers"
-    g = torch.Generator().manual_seed(40 + n2)
-    S = 12
-    e = torch.randn(S, 31, 128, generator=g)
-    h2 = torch.randn(S, 30, 128, generator=g)[:, :n2] if n2 else None
-    h_ref3, s_ref3 = O._star_cycles(P, pre, e, h2, 3, "multi_att_relay")
-    sat, relay = M.sublayer1(128, 8).to(dev), M.sublayer1(128, 8).to(dev)
-    with torch.no_grad():
-        for mod, name in ((sat, "multi_att_satellite"), (relay, "multi_att_relay")):
-            for w in ("wq", "wk", "wv"):
-                getattr(mod, w).kernel.copy_(P[f"{pre}/{name}/{w}/kernel"])
-            mod.dense.kernel.copy_(P[f"{pre}/{name}/dense/kernel"])
-            mod.dense.bias.copy_(P[f"{pre}/{name}/dense/bias"])
-    tile = L.star_pack(e.to(dev))
-    kv2 = None
-    if n2:
-        kv2 = torch.zeros(S, 30, 256, device=dev)
-        kv2[:, :n2] = L.linear(h2.reshape(-1, 128).to(dev), relay._packed("kv"), None, prec=prec).view(S, n2, 256)
-    x3 = M.star_cycles(tile, sat, relay, 3, kv2, n2)
-    torch.cuda.synchronize()
-    assert rel_err(x3[:, :31], h_ref3) < 4 * tol and rel_err(x3[:, 31], s_ref3) < 4 * tol
-
-
-@pytest.mark.parametrize("S", [8, 12, 40, 1188, 2372])
-def test_two_tile_star_kernel_is_bit_identical_to_the_one_tile_kernel(L, dev, S):
-    """Both forms issue the same UMMAs in the same order inside every job and run the same register code, so their results
-    must be EQUAL for every flag combination (first-satellite-half cached, no final relay), cycle count, key count and tile
-    count: odd tile counts (slot B one tile short), one CTA, every CTA with 2 / 4 / 5 tiles."""
-    import deepsc_gan_b200.models.modules as M
-    M.set_precision(1)
-    torch.manual_seed(S)
-    sat, relay = M.sublayer1(128, 8).to(dev), M.sublayer1(128, 8).to(dev)
-    tile = L.star_pack(torch.randn(S, 31, 128, device=dev))
-    ws = M.StarWorkspace(S, dev)
-    M.prepare_kv_e(tile, sat, ws, relay, first_sat=True)
-    pad = torch.zeros((S, 32, 256), device=dev)
-    pad[:, :30] = torch.randn(S, 30, 256, device=dev)
-    kv2i = L.star_interleave(pad, torch.empty_like(pad).view(-1), 32)
-
-    def run(cycles, n2, flags, form):
-        skip = bool(flags & L.STAR_FIRST_SAT_DONE)
-        out = torch.zeros(S, 32, 128, device=dev)
-        return L.star_cycles_tc(ws.xi1 if skip else ws.xi0, ws.s0, ws.q0, ws.kvei, kv2i if n2 else None, n2,
-                                sat._packed("qkv_grouped"), sat.dense.kernel.detach(), relay._packed("kv"),
-                                relay.dense.kernel.detach(), relay.wq.kernel.detach(), sat.dense.bias.detach(),
-                                relay.dense.bias.detach(), out, S, cycles, 1 | flags | form)
-
-    for cycles in (1, 2, 8) if S > 100 else (1, 2, 3, 8):
-        for flags in (0, L.STAR_NO_FINAL_RELAY, L.STAR_FIRST_SAT_DONE, L.STAR_FIRST_SAT_DONE | L.STAR_NO_FINAL_RELAY):
-            if (flags & L.STAR_FIRST_SAT_DONE) and cycles < 2:
-                continue
-            for n2 in (0, 17):
-                a = run(cycles, n2, flags, L.STAR_FORM_ONE_TILE)
-                b = run(cycles, n2, flags, L.STAR_FORM_TWO_TILE)
-                torch.cuda.synchronize()
-                rows = slice(0, 31) if (flags & L.STAR_NO_FINAL_RELAY) else slice(0, 32)
-                assert torch.equal(a[:, rows], b[:, rows]), (S, cycles, hex(flags), n2)
-
-
 @pytest.mark.parametrize("prec", [1, 2])
 @pytest.mark.parametrize("S,n2", [(8, 0), (12, 17), (600, 30)])
 def test_star_cycles_first_satellite_half_cached(L, dev, S, n2, prec, monkeypatch):

@@ -8,6 +8,8 @@ import deepsc_gan_b200  # noqa
 from deepsc_gan_b200 import _lib as L
 import deepsc_gan_b200.models.modules as M
 
+L.use_debug_library()          # the two-tile kernel is compiled into libdeepsc_b200_debug.so only
+
 dev = torch.device("cuda:0")
 M.set_precision(1)
 torch.manual_seed(0)
