@@ -10,7 +10,10 @@
 //   warp  8    UMMA issuer: 24 (8 for bf16) SS-mode UMMAs M = 128, N <= 256 into one of two TMEM accumulators;
 //   warps 9-16 epilogue: TMEM -> registers -> bias / ReLU -> y (two warps per TMEM lane quarter, alternate 32-column groups),
 //              overlapping the next tile's load + UMMAs.
-// Algorithmic bytes per row: 4 x (K + N) (x read once per 256-column slab, y written once).
+// K = 128 nk with nk > 1 (512 -> 128, 256 -> 16 of the same codec): the same roles walk (row tile, K chunk) pairs; a slab is
+// then 128 columns wide and its weights (64 KB per K chunk) stream from L2 through a two-stage ring filled by a producer
+// warp, the accumulator collects the chunks.
+// Algorithmic bytes per row: 4 x (K + N) (x read once per column slab, y written once).
 #include "dsc_common.cuh"
 #include "dsc_tc.cuh"
 
@@ -19,15 +22,15 @@ namespace dsc {
 using namespace tc;
 
 namespace k128 {
-constexpr int kLoaders = 8, kIssuer = 8, kEpi = 8, kThreads = 32 * (kLoaders + 1 + kEpi);   // 8 loader warps, issuer, 8 epilogue warps
+constexpr int kLoaders = 8, kIssuer = 8, kEpi = 8, kProducer = kLoaders + 1 + kEpi, kThreads = 32 * (kProducer + 1);   // 8 loader warps, issuer, 8 epilogue warps, weight producer
 constexpr uint32_t A_PLANE = 128 * 128;       // [part][kb] plane of the A operand: 128 rows x 128 B
-struct Bars { uint64_t b_full, a_full, a_free, acc_full[2], acc_free[2]; };
+struct Bars { uint64_t w_full[2], w_free[2], a_full, a_free, acc_full[2], acc_free[2]; };
 }  // namespace k128
 
 template <int NPASS>
 __global__ void __launch_bounds__(k128::kThreads, 1)
 gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint8_t* __restrict__ blob, int n_pad, int n0, int bn,
-                            const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int M, int N, int act) {
+                            const float* __restrict__ bias, float* __restrict__ y, int64_t ldy, int M, int N, int act, int nk) {
   using namespace k128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -45,7 +48,7 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
   const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   for (int i = tid; i < 256; i += kThreads) bias_s[i] = (bias != nullptr && i < bn && n0 + i < N) ? __ldg(bias + n0 + i) : 0.f;
   if (tid == 0) {
-    mbar_init(&bars.b_full, 1);
+    for (int st = 0; st < 2; ++st) { mbar_init(&bars.w_full[st], 1); mbar_init(&bars.w_free[st], 1); }
     mbar_init(&bars.a_full, kLoaders);
     mbar_init(&bars.a_free, 1);
     for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], kEpi); }
@@ -62,17 +65,19 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
     const int kb_l = lane >> 4;
     const uint32_t k_in = (uint32_t)((lane & 15) << 2);
     float4 v[16];
-    auto load_tile = [&](int t) {
-      const int m0 = t * 128;
+    const int n_chunks = my_tiles * nk;                     // (row tile, K chunk) pairs of this CTA, chunk-minor
+    auto load_chunk = [&](int g) {
+      const int i = g / nk, kc = g - i * nk;
+      const int m0 = (blockIdx.x + i * gridDim.x) * 128;
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         const int gr = m0 + warp + kLoaders * it;
-        v[it] = (gr < M) ? ld_stream(reinterpret_cast<const float4*>(x + (int64_t)gr * ldx) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[it] = (gr < M) ? ld_stream(reinterpret_cast<const float4*>(x + (int64_t)gr * ldx + kc * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if (my_tiles > 0) load_tile(blockIdx.x);
-    for (int i = 0; i < my_tiles; ++i) {
-      if (i > 0) mbar_wait(&bars.a_free, (uint32_t)(i - 1) & 1u);       // the UMMAs of the previous tile have read sA
+    if (n_chunks > 0) load_chunk(0);
+    for (int g = 0; g < n_chunks; ++g) {
+      if (g > 0) mbar_wait(&bars.a_free, (uint32_t)(g - 1) & 1u);       // the UMMAs of the previous chunk have read sA
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         uint32_t h0, l0, h1, l1;
@@ -85,26 +90,39 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a_full);
-      if (i + 1 < my_tiles) load_tile(blockIdx.x + (i + 1) * gridDim.x);   // in flight while this tile's UMMAs run
+      if (g + 1 < n_chunks) load_chunk(g + 1);                          // in flight while this chunk's UMMAs run
     }
-  } else if (warp == kIssuer) {
-    // ------------------------------------------------------------------ weights (once), then the UMMA issuer
-    if (lane == 0 && my_tiles > 0) {
-      mbar_expect_tx(&bars.b_full, parts * 2 * b_plane);
-      for (int p = 0; p < parts; ++p)
-        for (int kb = 0; kb < 2; ++kb)
-          bulk_g2s(sB + (p * 2 + kb) * b_plane, blob + ((size_t)(p * 2 + kb) * n_pad + (size_t)n0) * 128, b_plane, &bars.b_full);
+  } else if (warp == kProducer) {
+    // ------------------------------------------------------------------ weights: once (nk = 1) or a two-stage ring over the K chunks
+    if (lane == 0) {
+      const int n_loads = (nk == 1) ? (my_tiles > 0 ? 1 : 0) : my_tiles * nk;
+      const size_t kplane = (size_t)n_pad * 128;                        // one (part, K-block) plane of the blob
+      for (int g = 0; g < n_loads; ++g) {
+        const int st = g & 1, kc = g % nk;
+        mbar_wait(&bars.w_free[st], ((uint32_t)(g >> 1) - 1u) & 1u);
+        mbar_expect_tx(&bars.w_full[st], parts * 2 * b_plane);
+        uint8_t* dst = sB + (nk == 1 ? 0 : st * (parts * 2 * b_plane));
+        for (int p = 0; p < parts; ++p)
+          for (int kb = 0; kb < 2; ++kb)
+            bulk_g2s(dst + (p * 2 + kb) * b_plane, blob + ((size_t)(p * 2 * nk + 2 * kc + kb)) * kplane + (size_t)n0 * 128, b_plane, &bars.w_full[st]);
+      }
     }
     __syncwarp();
+  } else if (warp == kIssuer) {
+    // ------------------------------------------------------------------ UMMA issuer
     const bool leader = elect_one();
-    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+    const uint32_t a_base = smem_u32(sA), b_base0 = smem_u32(sB);
     const uint32_t idesc = idesc_bf16_f32(128, bn);
-    if (my_tiles > 0) mbar_wait(&bars.b_full, 0);
-    for (int i = 0; i < my_tiles; ++i) {
-      const uint32_t b = (uint32_t)i & 1u, use = (uint32_t)i >> 1;
-      mbar_wait(&bars.a_full, (uint32_t)i & 1u);
-      mbar_wait(&bars.acc_free[b], (use - 1) & 1u);                     // the epilogue drained this accumulator
+    const int n_chunks = my_tiles * nk;
+    if (nk == 1 && my_tiles > 0) mbar_wait(&bars.w_full[0], 0);
+    for (int g = 0; g < n_chunks; ++g) {
+      const int i = g / nk, kc = g - i * nk;
+      const uint32_t b = (uint32_t)i & 1u, use = (uint32_t)i >> 1, st = (uint32_t)g & 1u;
+      mbar_wait(&bars.a_full, (uint32_t)g & 1u);
+      if (nk > 1) mbar_wait(&bars.w_full[st], ((uint32_t)g >> 1) & 1u);
+      if (kc == 0) mbar_wait(&bars.acc_free[b], (use - 1) & 1u);        // the epilogue drained this accumulator
       tc_fence_after();
+      const uint32_t b_base = b_base0 + (nk == 1 ? 0u : st * (parts * 2 * b_plane));
       if (leader) {
 #pragma unroll
         for (int pass = 0; pass < NPASS; ++pass) {
@@ -114,14 +132,16 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
               umma_ss(tmem_base + b * 256u, smem_desc_sw128(a_base + (pa * 2 + kb) * A_PLANE + ks * 32u),
-                      smem_desc_sw128(b_base + (pb * 2 + kb) * b_plane + ks * 32u), idesc, (pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
+                      smem_desc_sw128(b_base + (pb * 2 + kb) * b_plane + ks * 32u), idesc,
+                      (kc > 0 || pass > 0 || kb > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(&bars.a_free);
-        umma_commit(&bars.acc_full[b]);
+        if (nk > 1) umma_commit(&bars.w_free[st]);
+        if (kc == nk - 1) umma_commit(&bars.acc_full[b]);
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp < kProducer) {
     // ------------------------------------------------------------------ epilogue: warps 9..16, TMEM lane quarter = warp & 3, two
     // warps per quarter taking alternate 32-column groups (one warp per scheduler was latency-bound: ~9 us per tile)
     const int quarter = warp & 3, e_half = (warp - kIssuer - 1) >> 2;
@@ -190,7 +210,7 @@ gemm_k128_persistent_kernel(const float* __restrict__ x, int64_t ldx, const uint
 
 template <int NPASS>
 static int launch_k128(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y, int64_t ldy,
-                       int M, int N, int act, cudaStream_t s) {
+                       int M, int K, int N, int act, cudaStream_t s) {
   constexpr int parts = (NPASS == 3) ? 2 : 1;
   constexpr size_t smem = (size_t)parts * 2 * 256 * 128 + (size_t)parts * 2 * 128 * 128 + k128::kEpi * 32 * 32 * 4 + 1024;
   static bool attr_set = false;
@@ -199,19 +219,20 @@ static int launch_k128(const float* x, int64_t ldx, const uint8_t* blob, int n_p
     if (e != cudaSuccess) { set_error("dsc_linear_tc: %s", cudaGetErrorString(e)); return DSC_ERR_CUDA; }
     attr_set = true;
   }
-  const int n_tiles = (M + 127) / 128;
+  const int n_tiles = (M + 127) / 128, nk = K / 128;
   const int grid = n_tiles < kSMs ? n_tiles : kSMs;
-  for (int n0 = 0; n0 < n_pad; n0 += 256) {                   // one launch per 256-column slab (x is re-read per slab)
-    const int bn = (n_pad - n0) < 256 ? (n_pad - n0) : 256;
-    gemm_k128_persistent_kernel<NPASS><<<grid, k128::kThreads, smem, s>>>(x, ldx, blob, n_pad, n0, bn, bias, y, ldy, M, N, act);
+  const int slab = (nk == 1) ? 256 : 128;                     // K > 128: the ring holds two 64 KB chunks of a 128-column slab
+  for (int n0 = 0; n0 < n_pad; n0 += slab) {                  // one launch per column slab (x is re-read per slab)
+    const int bn = (n_pad - n0) < slab ? (n_pad - n0) : slab;
+    gemm_k128_persistent_kernel<NPASS><<<grid, k128::kThreads, smem, s>>>(x, ldx, blob, n_pad, n0, bn, bias, y, ldy, M, N, act, nk);
   }
   return check_launch("dsc_linear_tc");
 }
 
 int linear_k128_persistent(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y, int64_t ldy,
-                           int M, int N, int act, int npass, cudaStream_t s) {
-  return npass == 3 ? launch_k128<3>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, s)
-                    : launch_k128<1>(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, s);
+                           int M, int K, int N, int act, int npass, cudaStream_t s) {
+  return npass == 3 ? launch_k128<3>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, s)
+                    : launch_k128<1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, s);
 }
 
 }  // namespace dsc

@@ -307,7 +307,7 @@ static int launch_gemm_tc(const float* x, int64_t ldx, const uint8_t* blob, int 
 }
 
 int linear_k128_persistent(const float* x, int64_t ldx, const uint8_t* blob, int n_pad, const float* bias, float* y, int64_t ldy,
-                           int M, int N, int act, int npass, cudaStream_t s);   // dsc_gemm_k128.cu
+                           int M, int K, int N, int act, int npass, cudaStream_t s);   // dsc_gemm_k128.cu
 
 int linear_tc(const float*, int64_t, const float*, int64_t, const float*, float*, int64_t, int, int, int, int, int, int,
               int prec, cudaStream_t) {
@@ -360,9 +360,9 @@ extern "C" int dsc_linear_tc(const float* x, int64_t ldx, const void* packed_w, 
   // many row tiles (the channel codec's 73,408-row layers): 64 KB CTAs, three per SM, so that the phases of different
   // tiles overlap; few tiles (a greedy step's 2,368 rows): one CTA per SM with the whole K = 128 chunk in one pass
   const bool many = (int64_t)((M + TC_BM - 1) / TC_BM) * (n_pad / 128) >= 2 * kSMs;
-  // K = 128 with at least two row tiles per SM: the persistent kernel (weights resident, row tiles streamed)
-  if (K == 128 && row_mod == 0 && (M + TC_BM - 1) / TC_BM >= 2 * kSMs && !(prec_flags & 64))
-    return linear_k128_persistent(x, ldx, blob, n_pad, bias, y, ldy, M, N, act, prec == 1 ? 3 : 1, s);
+  // at least two row tiles per SM: the persistent kernel (K = 128: weights resident; K = 256 .. 512: weight chunks ringed)
+  if ((K == 128 || (K <= 512 && n_pad <= 256)) && row_mod == 0 && (M + TC_BM - 1) / TC_BM >= 2 * kSMs && !(prec_flags & 64))
+    return linear_k128_persistent(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, prec == 1 ? 3 : 1, s);
   if (many)
     return prec == 1 ? launch_gemm_tc<128, 3, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s)
                      : launch_gemm_tc<128, 1, 1>(x, ldx, blob, n_pad, bias, y, ldy, M, K, N, act, row_mod, row_skip, s);
